@@ -1,0 +1,197 @@
+/*
+ * zaremba_b200.h -- C ABI of libzaremba_b200.so: the B200 (sm_100a) implementation of
+ * the LSTM language-model hot path of ahmetumutdurmus/zaremba.
+ *
+ * The reference has no native boundary (it is three Python files calling PyTorch), so
+ * the entry points below are what a binding for this path would bind; each one cites
+ * the reference lines it replaces (paths relative to /root/reference).  INTEGRATION.md
+ * shows the ctypes stub a maintainer adds to `model.py`.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name starts with
+ *     `h_` (host).  The caller owns all buffers it passes; the library owns only the
+ *     context it creates (activation workspace, low-precision weight images).
+ *   - every function returns 0 on success or a negative ZRB_E_* code;
+ *     zrb_last_error() returns a thread-local message for the last failure.
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises unless documented.  One context per thread / stream.
+ *   - tokens n = t*B + b (t-major), exactly how `x.view(-1, H)` / `y.reshape(-1)`
+ *     flatten [T,B] in model.py:67 and main.py:81.
+ *   - gate row blocks follow torch.nn.LSTM: (i, f, g, o).
+ */
+#ifndef ZAREMBA_B200_H
+#define ZAREMBA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZRB_OK            0
+#define ZRB_E_INVALID    -1   /* bad argument / unsupported shape            */
+#define ZRB_E_CUDA       -2   /* a CUDA runtime / driver call failed         */
+#define ZRB_E_STATE      -3   /* call order (e.g. backward without forward)  */
+#define ZRB_E_NOMEM      -4
+
+#define ZRB_MAX_LAYERS    8
+
+/* engines: how the dense contractions are executed */
+#define ZRB_ENGINE_SIMT   0   /* fp32 CUDA-core GEMMs; validation engine                    */
+#define ZRB_ENGINE_TC     1   /* tcgen05 tensor cores, fp16 operands, fp32 accumulation     */
+
+typedef struct zrb_ctx zrb_ctx;   /* opaque */
+
+/* Shape of the model, i.e. the constructor arguments of `Model` (model.py:76) plus the
+ * largest [T,B] window the context must hold activations for. */
+typedef struct {
+    int32_t vocab;        /* V  */
+    int32_t hidden;       /* H  */
+    int32_t layers;       /* L  (<= ZRB_MAX_LAYERS) */
+    int32_t max_seq;      /* T  upper bound */
+    int32_t max_batch;    /* B  upper bound */
+    int32_t engine;       /* ZRB_ENGINE_*   */
+    float   dropout;      /* p of nn.Dropout (model.py:87) */
+    int32_t reserved;
+} zrb_config;
+
+/* The 11 (= 3 + 4L) parameter tensors in the reference's registration order
+ * (model.py:83-86): fp32, row-major, contiguous. */
+typedef struct {
+    float* embed_w;                       /* [V,H]   embed.W              model.py:11 */
+    float* w_ih[ZRB_MAX_LAYERS];          /* [4H,H]  rnns.l.weight_ih_l0  model.py:84 */
+    float* w_hh[ZRB_MAX_LAYERS];          /* [4H,H]  rnns.l.weight_hh_l0              */
+    float* b_ih[ZRB_MAX_LAYERS];          /* [4H]    rnns.l.bias_ih_l0                */
+    float* b_hh[ZRB_MAX_LAYERS];          /* [4H]    rnns.l.bias_hh_l0                */
+    float* fc_w;                          /* [V,H]   fc.W                 model.py:62 */
+    float* fc_b;                          /* [V]     fc.b                 model.py:63 */
+} zrb_params;
+
+/* (h, c) entering / leaving the BPTT window: model.py:94-98.  [B,H] fp32 each (the
+ * pytorch path's [1,B,H] has the same bytes). */
+typedef struct {
+    float* h[ZRB_MAX_LAYERS];
+    float* c[ZRB_MAX_LAYERS];
+} zrb_states;
+
+const char* zrb_last_error(void);
+const char* zrb_version(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t     zrb_launch_count(void);
+
+int  zrb_ctx_create(const zrb_config* cfg, zrb_ctx** out);
+void zrb_ctx_destroy(zrb_ctx* ctx);
+/* bytes of device memory the context holds */
+int64_t zrb_ctx_workspace_bytes(const zrb_ctx* ctx);
+
+/* Tell the context that parameter values changed outside the library (main.py:116-117
+ * updates them in place), so low-precision weight images must be rebuilt on next use. */
+int  zrb_params_changed(zrb_ctx* ctx);
+
+/* Dropout: keep-masks are a pure function of (seed, step, site, element) through
+ * Philox4x32-10, so backward regenerates them.  `site` 0 = after the embedding,
+ * l+1 = after layer l (the three call sites of model.py:105,108).
+ * zrb_dropout_mask writes the keep-mask (1 = keep) the kernels will use, so a test can
+ * hand the same mask to the oracle. */
+int  zrb_dropout_mask(uint64_t seed, uint64_t step, int32_t site, int64_t n, float p,
+                      uint8_t* mask_out, void* stream);
+/* Optional: force explicit keep-masks instead of Philox (L+1 sites, each [T*B*H] bytes,
+ * 1 = keep).  Pass NULL to return to Philox.  Used to replay the reference's masks. */
+int  zrb_set_explicit_masks(zrb_ctx* ctx, const uint8_t* const* site_masks);
+
+/* Model.forward (model.py:103-110): embedding gather, dropout, L x (LSTM layer,
+ * dropout), vocabulary projection.
+ *   x        [T,B] int64 token ids, t-major contiguous
+ *   in/out   states entering / leaving the window (may alias)
+ *   scores   [T*B, V] fp32 (model.py:109), or NULL to skip the projection
+ *   train    nonzero = nn.Dropout active (module in .train()), activations kept for backward
+ */
+int  zrb_forward(zrb_ctx* ctx, const zrb_params* p, const int64_t* x, int32_t T, int32_t B,
+                 const zrb_states* in, const zrb_states* out, float* scores,
+                 int32_t train, uint64_t seed, uint64_t step, void* stream);
+
+/* What autograd derives for model.py:103-110 given d loss / d scores (main.py:113).
+ *   dscores  [T*B, V] fp32
+ *   grads    dense gradients, same shapes as the parameters; OVERWRITTEN (not accumulated)
+ */
+int  zrb_backward(zrb_ctx* ctx, const zrb_params* p, const float* dscores,
+                  const zrb_params* grads, void* stream);
+
+/* nll_loss (main.py:77-84) and its gradient in one pass over the scores:
+ *   loss      1 float: mean_n(-log softmax(scores)[n, y_n]) * B
+ *   dscores   [N,V] fp32 (softmax - onehot) * B / N, or NULL
+ *   tgt_prob  [N] fp32 softmax(scores)[n, y_n], or NULL (ensemble.py:100-106 needs it)
+ */
+int  zrb_softmax_nll(zrb_ctx* ctx, const float* scores, const int64_t* y, int32_t T, int32_t B,
+                     float* loss, float* dscores, float* tgt_prob, void* stream);
+
+/* clip_grad_norm_ + SGD (main.py:114-117) over n tensors:
+ *   norm = sqrt(sum ||g||^2); coef = min(1, max_norm / (norm + 1e-6)); g *= coef; p -= lr*g
+ *   norm_out  1 float (pre-clip norm, main.py:115) */
+int  zrb_clip_sgd(zrb_ctx* ctx, int32_t n, float* const* params, float* const* grads,
+                  const int64_t* sizes, float lr, float max_norm, float* norm_out, void* stream);
+
+/* One whole iteration of main.py:109-117 without leaving the library (the data-parallel
+ * hook sits between the two halves: gradients are complete after _grads, the caller may
+ * all-reduce them, then _update clips on the global norm and applies SGD).
+ *   y [T,B] int64; loss / norm: 1 float each */
+int  zrb_train_step_grads(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,
+                          const int64_t* x, const int64_t* y, int32_t T, int32_t B,
+                          const zrb_states* in, const zrb_states* out,
+                          uint64_t seed, uint64_t step, float* loss, void* stream);
+int  zrb_train_step_update(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,
+                           float lr, float max_norm, float* norm_out, void* stream);
+
+/* perplexity's inner step (main.py:91-94) without materialising scores for the caller:
+ * forward in eval mode + loss (+ per-token target probabilities for the ensemble). */
+int  zrb_eval_step(zrb_ctx* ctx, const zrb_params* p, const int64_t* x, const int64_t* y,
+                   int32_t T, int32_t B, const zrb_states* in, const zrb_states* out,
+                   float* loss, float* tgt_prob, void* stream);
+
+/* Same as zrb_train_step_grads + zrb_train_step_update but with HOST token buffers
+ * (pinned or pageable) and a host loss: the H2D copies of x, y and the D2H copy of the
+ * loss are issued on `stream` inside the call; the call returns after the loss landed. */
+int  zrb_train_step_host(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,
+                         const int64_t* h_x, const int64_t* h_y, int32_t T, int32_t B,
+                         const zrb_states* in, const zrb_states* out,
+                         uint64_t seed, uint64_t step, float lr, float max_norm,
+                         float* h_loss, float* h_norm, void* stream);
+
+/* Per-kernel-class timing with CUDA events recorded on the launching stream (bench.py's
+ * `roofline` leg).  While enabled, every kernel class below is bracketed by an event pair.
+ * zrb_prof_read synchronises, writes total milliseconds and launch-group counts per class
+ * (arrays of ZRB_PROF_COUNT) and resets the accumulators. */
+#define ZRB_PROF_EMBED_FWD    0   /* embedding gather + dropout                       */
+#define ZRB_PROF_GEMM_IN      1   /* input-to-hidden GEMM  X * W_ih^T (all T at once)  */
+#define ZRB_PROF_REC_FWD      2   /* recurrence over T: h * W_hh^T + cell pointwise    */
+#define ZRB_PROF_PROJ_FWD     3   /* vocabulary projection                             */
+#define ZRB_PROF_SOFTMAX      4   /* softmax-NLL fwd+bwd                               */
+#define ZRB_PROF_PROJ_BWD     5   /* projection dgrad + wgrad + bias grad              */
+#define ZRB_PROF_REC_BWD      6   /* reverse recurrence: cell bwd + dG * W_hh          */
+#define ZRB_PROF_GEMM_DX      7   /* dG * W_ih                                         */
+#define ZRB_PROF_GEMM_WGRAD   8   /* dW_ih, dW_hh, bias grads                          */
+#define ZRB_PROF_EMBED_BWD    9   /* embedding scatter-add                             */
+#define ZRB_PROF_CLIP_SGD    10   /* grad norm + clip + SGD (+ weight image refresh)   */
+#define ZRB_PROF_PACK        11   /* low-precision weight image build                  */
+#define ZRB_PROF_COUNT       12
+int  zrb_prof_enable(zrb_ctx* ctx, int32_t on);
+int  zrb_prof_read(zrb_ctx* ctx, float* h_ms, int64_t* h_counts);
+
+/* ---- building blocks, exported for unit tests and profiling ------------------------ */
+
+/* C[M,N] = alpha * A[M,K] * op(B) + beta * C  in fp32 on CUDA cores.
+ * transB != 0: B is [N,K] (C = A * B^T);  transB == 0: B is [K,N].
+ * transA != 0: A is stored [K,M]. */
+int  zrb_gemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
+                  int32_t transA, int32_t transB, float alpha, float beta, void* stream);
+
+/* C[M,N] (fp32) = alpha * A[M,K] * B[N,K]^T (+ bias[N]) on tcgen05 tensor cores.
+ * A, B: fp16, K contiguous, leading dimensions lda/ldb in elements (multiples of 8). */
+int  zrb_gemm_f16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
+                     float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                     float alpha, const float* bias, int32_t accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZAREMBA_B200_H */

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via zaremba_b200.Model / Trainer and
+direct ctypes calls) against the reference fixtures and the numpy oracle.
+
+Tolerances (stated per engine):
+  simt  fp32 CUDA-core engine: differs from the fp32 reference only by summation order
+        -> 5e-5 relative to the tensor's scale.
+  tc    tcgen05 engine: fp16 operands (11-bit significand, the same as the TF32 the
+        reference's own cuDNN path uses on GPU), fp32 accumulation -> 4e-3 relative to the
+        tensor's scale on logits/states, 1.5e-2 on gradients ("Numerics").
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstm_lm_oracle as O
+from tests._golden import GOLDEN, STEP_CASES, StepCase
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = os.environ.get("ZRB_TEST_ENGINES", "simt,tc").split(",")
+TOL = {"simt": dict(fwd=5e-5, grad=1e-4, loss=2e-5), "tc": dict(fwd=4e-3, grad=1.5e-2, loss=2e-3)}
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _scale_close(got, want, rel, what):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    scale = max(np.abs(want).max(), 1e-6)
+    err = np.abs(got - want).max()
+    assert err <= rel * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.2e} > {rel:.1e})"
+
+
+def _caller_nll_loss(scores, y):
+    """what main.py:77-84 does with our scores (torch ops on the CALLER's side of the boundary)."""
+    B = y.size(1)
+    e = scores.exp()
+    p = e / e.sum(1, keepdim=True)
+    yy = y.reshape(-1).to(scores.device)
+    return torch.mean(-torch.log(p[torch.arange(yy.numel(), device=scores.device), yy]) * B)
+
+
+def _model_from_case(c, engine, lstm_type=None):
+    import zaremba_b200
+    lstm_type = lstm_type or c.lstm_type
+    m = zaremba_b200.Model(c.V, c.H, c.L, c.dropout, c.winit, lstm_type, engine=engine)
+    raw = {k[len("param0/"):]: c.z[k] for k in c.z.files if k.startswith("param0/")}
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(raw), (sorted(sd), sorted(raw))
+    m.load_state_dict({k: torch.tensor(v) for k, v in raw.items()})
+    return m.to(_dev())
+
+
+def _states_to_model(c, m):
+    sts = []
+    for h, cc in c.states0():
+        shape = (c.B, c.H) if m.lstm_type == "custom" else (1, c.B, c.H)
+        sts.append((torch.tensor(h).view(shape).to(_dev()), torch.tensor(cc).view(shape).to(_dev())))
+    return sts
+
+
+def _grads_pytorch_order(c, m):
+    g = {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters()}
+    return O.custom_state_dict_to_pytorch(g) if c.lstm_type == "custom" else g
+
+
+def _params_pytorch_order(c, m):
+    g = {k: p.detach().cpu().numpy() for k, p in m.named_parameters()}
+    return O.custom_state_dict_to_pytorch(g) if c.lstm_type == "custom" else g
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_dropin_train_steps_match_reference(name, engine):
+    """The reference's own loop (main.py:109-117) run against the drop-in Model, compared
+    with what the reference recorded for the same weights, tokens, states and dropout masks."""
+    c = StepCase(name)
+    tol = TOL[engine]
+    m = _model_from_case(c, engine)
+    m.train() if c.dropout > 0 else m.eval()
+    states = _states_to_model(c, m)
+    for s in range(c.steps):
+        x = torch.tensor(c.x(s)).t().contiguous().t()      # non-contiguous CPU view like main.py:71
+        y = torch.tensor(c.y(s)).t().contiguous().t()
+        if c.dropout > 0:
+            m.set_explicit_dropout_masks([torch.tensor(mk).to(_dev()) for mk in c.masks(s)])
+        m.zero_grad()
+        states = m.detach(states)
+        scores, states = m(x, states)
+        loss = _caller_nll_loss(scores, y)
+        loss.backward()
+        _scale_close(scores.detach().cpu().numpy(), c.scores(s), tol["fwd"], f"{name} s{s} scores")
+        assert abs(loss.item() - c.loss(s)) <= tol["loss"] * max(1.0, abs(c.loss(s)))
+        grads = _grads_pytorch_order(c, m)
+        ref_grads = c.grads(s)
+        for k in c.names:
+            _scale_close(grads[k], ref_grads[k], tol["grad"], f"{name} s{s} grad {k}")
+        with torch.no_grad():
+            norm = torch.nn.utils.clip_grad_norm_(m.parameters(), c.max_norm)
+            for p in m.parameters():
+                p -= c.lr * p.grad
+        assert abs(float(norm) - c.norm(s)) <= tol["grad"] * max(1.0, c.norm(s))
+        after = _params_pytorch_order(c, m)
+        ref_after = c.params_after(s)
+        for k in c.names:
+            _scale_close(after[k], ref_after[k], tol["grad"], f"{name} s{s} param {k}")
+        for l, (h, cc) in enumerate(c.states_after(s)):
+            _scale_close(states[l][0].reshape(c.B, c.H).cpu().numpy(), h, tol["fwd"], f"{name} s{s} h{l}")
+            _scale_close(states[l][1].reshape(c.B, c.H).cpu().numpy(), cc, tol["fwd"], f"{name} s{s} c{l}")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["tiny_pytorch", "tiny_dropout", "tiny_carry3", "mid_H72", "edge_T1_B1_L1"])
+def test_fused_trainer_matches_reference(name, engine):
+    """zrb_train_step_grads + zrb_train_step_update (one library call per half step)."""
+    import zaremba_b200
+    c = StepCase(name)
+    tol = TOL[engine]
+    m = _model_from_case(c, engine)
+    m.train()
+    tr = zaremba_b200.Trainer(m, c.B, c.T)
+    for l, (h, cc) in enumerate(c.states0()):
+        tr.states[l][0].copy_(torch.tensor(h).view_as(tr.states[l][0]))
+        tr.states[l][1].copy_(torch.tensor(cc).view_as(tr.states[l][1]))
+    for s in range(c.steps):
+        x = torch.tensor(c.x(s)).to(_dev()).contiguous()
+        y = torch.tensor(c.y(s)).to(_dev()).contiguous()
+        if c.dropout > 0:
+            m.set_explicit_dropout_masks([torch.tensor(mk).to(_dev()) for mk in c.masks(s)])
+        loss, norm = tr.train_step(x, y, c.lr, c.max_norm)
+        assert abs(loss.item() - c.loss(s)) <= tol["loss"] * max(1.0, abs(c.loss(s)))
+        assert abs(norm.item() - c.norm(s)) <= tol["grad"] * max(1.0, c.norm(s))
+        after = _params_pytorch_order(c, m)
+        ref_after = c.params_after(s)
+        for k in c.names:
+            _scale_close(after[k], ref_after[k], tol["grad"], f"{name} s{s} param {k}")
+        for l, (h, cc) in enumerate(c.states_after(s)):
+            _scale_close(tr.states[l][0].reshape(c.B, c.H).cpu().numpy(), h, tol["fwd"], f"{name} s{s} h{l}")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_host_buffer_step_equals_device_step(engine):
+    """zrb_train_step_host (H2D/D2H inside) == device-token step, bit for bit in eval of loss."""
+    import zaremba_b200
+    c = StepCase("mid_H72")
+    outs = []
+    for mode in ("dev", "host"):
+        m = _model_from_case(c, engine)
+        m.train()
+        tr = zaremba_b200.Trainer(m, c.B, c.T)
+        x, y = torch.tensor(c.x(0)), torch.tensor(c.y(0))
+        if mode == "dev":
+            loss, norm = tr.train_step(x.to(_dev()).contiguous(), y.to(_dev()).contiguous(), c.lr, c.max_norm)
+            outs.append((loss.item(), norm.item(), tr.flat_p.clone()))
+        else:
+            loss, norm = tr.train_step_host(x.t().contiguous().t(), y.t().contiguous().t(), c.lr, c.max_norm)
+            outs.append((loss, norm, tr.flat_p.clone()))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[0][0])
+    assert abs(outs[0][1] - outs[1][1]) <= 1e-5 * abs(outs[0][1])
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=0, atol=1e-6)
+
+
+def test_gemm_f32_matches_numpy():
+    from zaremba_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for (M, N, K, ta, tb) in [(5, 7, 3, 0, 1), (64, 64, 16, 0, 0), (70, 130, 33, 1, 0), (20, 6000, 1500, 0, 1),
+                              (1, 1, 1, 1, 1), (129, 65, 257, 1, 1)]:
+        A = rng.normal(size=(K, M) if ta else (M, K)).astype(np.float32)
+        Bm = rng.normal(size=(N, K) if tb else (K, N)).astype(np.float32)
+        C0 = rng.normal(size=(M, N)).astype(np.float32)
+        a, b, c = (torch.tensor(v).cuda() for v in (A, Bm, C0))
+        _lib.check(lib.zrb_gemm_f32(_lib.ptr(a), _lib.ptr(b), _lib.ptr(c), M, N, K, ta, tb, 0.5, 2.0, None))
+        want = 0.5 * ((A.T if ta else A).astype(np.float64) @ (Bm.T if tb else Bm).astype(np.float64)) + 2.0 * C0
+        _scale_close(c.cpu().numpy(), want, 2e-6 * max(1, K ** 0.5), f"gemm {M}x{N}x{K}")
+
+
+def test_softmax_nll_against_oracle_and_properties():
+    """zrb_softmax_nll vs main.py:77-84 restated; gradient rows sum to ~0; target prob in (0,1]."""
+    from zaremba_b200 import _lib
+    import zaremba_b200
+    lib = _lib.load()
+    T, B, V = 35, 20, 10000
+    m = zaremba_b200.Model(V, 8, 1, 0.0, 0.1, engine="simt").to(_dev())
+    ctx = m._context(T, B)
+    rng = np.random.default_rng(3)
+    s = (rng.normal(size=(T * B, V)) * 3).astype(np.float32)
+    y = rng.integers(0, V, size=(T, B))
+    sd, yd = torch.tensor(s).cuda(), torch.tensor(y).cuda()
+    loss = torch.zeros((), device="cuda"); ds = torch.empty_like(sd); tp = torch.empty(T * B, device="cuda")
+    _lib.check(lib.zrb_softmax_nll(ctx, _lib.ptr(sd), _lib.ptr(yd), T, B, _lib.ptr(loss), _lib.ptr(ds), _lib.ptr(tp), None))
+    want = O.nll_loss(s.astype(np.float64), y)
+    assert abs(loss.item() - want) < 2e-6 * want
+    _scale_close(ds.cpu().numpy(), O.nll_loss_bwd(s.astype(np.float64), y), 2e-5, "dscores")
+    _scale_close(tp.cpu().numpy(), O.target_probs(s.astype(np.float64), y), 2e-5, "target probs")
+    assert ds.sum(1).abs().max().item() < 1e-6
+    assert (tp > 0).all() and (tp <= 1).all()
+
+
+def test_clip_sgd_matches_oracle():
+    from zaremba_b200 import _lib
+    import zaremba_b200
+    lib = _lib.load()
+    m = zaremba_b200.Model(11, 8, 1, 0.0, 0.1, engine="simt").to(_dev())
+    ctx = m._context(2, 2)
+    rng = np.random.default_rng(5)
+    sizes = [1, 7, 1000003, 64, 12345]
+    for max_norm in (1e9, 3.0):
+        ps = [rng.normal(size=n).astype(np.float32) for n in sizes]
+        gs = [rng.normal(size=n).astype(np.float32) * 0.01 for n in sizes]
+        pd = [torch.tensor(v).cuda() for v in ps]; gd = [torch.tensor(v).cuda() for v in gs]
+        names = [str(i) for i in range(len(sizes))]
+        pp = dict(zip(names, [v.copy() for v in ps])); gg = dict(zip(names, [v.copy() for v in gs]))
+        want_norm = O.clip_sgd(pp, gg, 0.7, max_norm, names)
+        arr_p = (C.c_void_p * len(sizes))(*[t.data_ptr() for t in pd])
+        arr_g = (C.c_void_p * len(sizes))(*[t.data_ptr() for t in gd])
+        arr_n = (C.c_int64 * len(sizes))(*sizes)
+        norm = torch.zeros((), device="cuda")
+        _lib.check(lib.zrb_clip_sgd(ctx, len(sizes), arr_p, arr_g, arr_n, 0.7, max_norm, _lib.ptr(norm), None))
+        assert abs(norm.item() - want_norm) < 1e-5 * want_norm
+        for i, n in enumerate(names):
+            np.testing.assert_allclose(pd[i].cpu().numpy(), pp[n], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(gd[i].cpu().numpy(), gg[n], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_philox_dropout_masks_replay_in_oracle(engine):
+    """Train-mode step with the library's own Philox masks: fetch the masks through
+    zrb_dropout_mask, hand them to the oracle, compare scores and gradients; also check
+    the keep rate."""
+    from zaremba_b200 import _lib
+    import zaremba_b200
+    lib = _lib.load()
+    V, H, L, T, B, p = 97, 48, 2, 6, 5, 0.65
+    torch.manual_seed(21)
+    m = zaremba_b200.Model(V, H, L, p, 0.2, engine=engine).to(_dev())
+    m.train()
+    rng = np.random.default_rng(2)
+    x = torch.tensor(rng.integers(0, V, size=(T, B))); y = torch.tensor(rng.integers(0, V, size=(T, B)))
+    states = m.state_init(B)
+    scores, states = m(x, states)
+    loss = _caller_nll_loss(scores, y)
+    loss.backward()
+    seed, step = m._seed, m._drop_step - 1
+    masks = []
+    for site in range(L + 1):
+        buf = torch.empty(T * B * H, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.zrb_dropout_mask(seed, step, site, T * B * H, p, _lib.ptr(buf), None))
+        masks.append(buf.cpu().numpy().reshape(T, B, H).astype(bool))
+    keep = np.mean([mk.mean() for mk in masks])
+    assert abs(keep - (1 - p)) < 0.03
+    assert not np.array_equal(masks[0], masks[1])
+    params = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in m.named_parameters()}
+    sc, _, cache = O.model_fwd(params, x.numpy(), O.zero_states(L, B, H, np.float64), L, p, masks)
+    grads = O.model_bwd(params, cache, O.nll_loss_bwd(sc, y.numpy()), L)
+    tol = TOL[engine]
+    _scale_close(scores.detach().cpu().numpy(), sc, tol["fwd"], "scores (philox masks)")
+    for k, prm in m.named_parameters():
+        _scale_close(prm.grad.cpu().numpy(), grads[k], tol["grad"], f"grad {k}")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_large_config_against_fp64_oracle(engine):
+    """BASELINE.json configs[2] shape (2x1500, T=35, B=20, V=10000), eval mode: logits, loss and
+    final states vs the fp64 oracle; plus size-independent properties (determinism,
+    linearity of backward in dscores)."""
+    import zaremba_b200
+    V, H, L, T, B = 10000, 1500, 2, 35, 20
+    torch.manual_seed(1)
+    m = zaremba_b200.Model(V, H, L, 0.65, 0.04, engine=engine).to(_dev())
+    m.eval()
+    g = torch.Generator().manual_seed(2)
+    data = torch.randint(0, V, (B, T + 1), generator=g)
+    x, y = data[:, :T].t(), data[:, 1:].t()
+    scores, states = m(x, m.state_init(B))
+    scores2, _ = m(x, m.state_init(B))
+    assert torch.equal(scores, scores2), "forward is not deterministic"
+    params = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in m.named_parameters()}
+    sc, st, cache = O.model_fwd(params, x.numpy(), O.zero_states(L, B, H, np.float64), L)
+    tol = TOL[engine]
+    _scale_close(scores.detach().cpu().numpy(), sc, tol["fwd"], "L logits")
+    for l in range(L):
+        _scale_close(states[l][0].reshape(B, H).cpu().numpy(), st[l][0], tol["fwd"], f"L h{l}")
+        _scale_close(states[l][1].reshape(B, H).cpu().numpy(), st[l][1], tol["fwd"], f"L c{l}")
+    loss = _caller_nll_loss(scores, y)
+    want = O.nll_loss(sc, y.numpy())
+    assert abs(loss.item() - want) < tol["loss"] * want
+    # backward: linear in dscores
+    loss.backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad()
+    scores, _ = m(x, m.state_init(B))
+    (2.0 * _caller_nll_loss(scores, y)).backward()
+    for k, p in m.named_parameters():
+        assert torch.allclose(p.grad, 2.0 * g1[k], rtol=1e-3, atol=1e-7 + 1e-4 * g1[k].abs().max().item()), k
+    grads = O.model_bwd(params, cache, O.nll_loss_bwd(sc, y.numpy()), L)
+    for k in grads:
+        _scale_close(g1[k].cpu().numpy(), grads[k], tol["grad"], f"L grad {k}")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_perplexity_and_ensemble_on_ptb_slice(engine):
+    """main.py:86-95 and ensemble.py:97-109 through Trainer.perplexity / eval_step."""
+    import zaremba_b200
+    z = np.load(os.path.join(GOLDEN, "perplexity_ptb_slice.npz"))
+    V, H, L, T, B = [int(v) for v in z["meta"]]
+    ms = []
+    for pre in ("param/", "param2/"):
+        m = zaremba_b200.Model(V, H, L, 0.0, 0.1, engine=engine)
+        m.load_state_dict({k[len(pre):]: torch.tensor(z[k]) for k in z.files if k.startswith(pre)})
+        ms.append(m.to(_dev()).eval())
+    ds = zaremba_b200.minibatch(z["ids"], B, T)
+    assert len(ds) == int(z["n_batches"])
+    tr = zaremba_b200.Trainer(ms[0], B, T)
+    ppl = tr.perplexity(ds)
+    assert abs(ppl - float(z["ppl"])) < TOL[engine]["loss"] * float(z["ppl"])
+    x, y = ds[0]
+    probs = []
+    for m in ms:
+        t = zaremba_b200.Trainer(m, B, T)
+        _, tp = t.eval_step(x.to(_dev()).contiguous(), y.to(_dev()).contiguous(), want_probs=True)
+        probs.append(tp.clone())
+    ens = torch.mean(-torch.log(torch.stack(probs).mean(0)) * B).item()
+    assert abs(ens - float(z["ens_loss"])) < TOL[engine]["loss"] * abs(float(z["ens_loss"]))
+
+
+def test_error_paths():
+    """Reference-like error behaviour: bad shapes / call order raise instead of corrupting memory."""
+    import zaremba_b200
+    from zaremba_b200 import _lib
+    m = zaremba_b200.Model(13, 8, 1, 0.0, 0.1, engine="simt")
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 2, dtype=torch.long), m.state_init(2))        # CPU model: no fallback
+    m = m.to(_dev())
+    lib = _lib.load()
+    ctx = m._context(2, 2)
+    ps, _ = m._params_struct(m.ordered_parameters())
+    rc = lib.zrb_backward(ctx, C.byref(ps), C.c_void_p(1), C.byref(ps), None)
+    assert rc == -3 and b"forward" in lib.zrb_last_error()
+    cfg = _lib.ZrbConfig(0, 8, 1, 2, 2, 0, 0.0, 0)
+    h = C.c_void_p()
+    assert lib.zrb_ctx_create(C.byref(cfg), C.byref(h)) == -1

@@ -1,0 +1,79 @@
+// Context layout and the two engines' entry points (internal).
+#pragma once
+#include <vector>
+
+#include "kernels.h"
+
+struct zrb_tc_state;  // tcgen05 engine private data (engine_tc.cu)
+
+struct zrb_ctx {
+    zrb_config cfg{};
+    std::vector<void*> allocs;
+    int64_t bytes = 0;
+
+    // activations kept between forward and backward (fp32, token-major [N, .])
+    float* act[ZRB_MAX_LAYERS + 1] = {};   // act[0] = dropout(embed(x)); act[l+1] = dropout(h of layer l)
+    float* gates[ZRB_MAX_LAYERS] = {};     // [N,4H] activated (i,f,g,o)
+    float* cst[ZRB_MAX_LAYERS] = {};       // [N,H]  c_t
+    float* hraw[ZRB_MAX_LAYERS] = {};      // [N,H]  h_t before dropout
+    float* h0s[ZRB_MAX_LAYERS] = {};       // [B,H]  state entering the window
+    float* c0s[ZRB_MAX_LAYERS] = {};
+    // backward scratch
+    float* dy = nullptr;                   // [N,H]
+    float* dx = nullptr;                   // [N,H]
+    float* dG = nullptr;                   // [N,4H]
+    float* dh_rec = nullptr;               // [B,H]
+    float* dc = nullptr;                   // [B,H]
+    // loss / optimiser scratch
+    float* row_loss = nullptr;             // [N]
+    float* partials = nullptr;
+    float* scalars = nullptr;
+    int64_t* x_saved = nullptr;            // [N] token ids of the last forward
+    int64_t* x_dev = nullptr;              // staging for host-buffer entry points
+    int64_t* y_dev = nullptr;
+    float* scores = nullptr;               // [N,V] used by the fused step / eval
+    float* dscores = nullptr;              // [N,V]
+
+    int T = 0, B = 0, train = 0;
+    uint64_t seed = 0, step = 0;
+    bool have_fwd = false;
+    bool explicit_masks_set = false;
+    const uint8_t* explicit_masks[ZRB_MAX_LAYERS + 1] = {};
+    int64_t weights_version = 1;           // bumped whenever parameter values change
+
+    zrb_tc_state* tc = nullptr;
+
+    // optional per-class event timing (zrb_prof_*)
+    bool prof_on = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+};
+
+namespace zrb {
+
+MaskSrc site_mask(const zrb_ctx* c, int site);
+
+// RAII bracket: records an event pair around the launches of one kernel class
+struct ProfScope {
+    zrb_ctx* c; cudaStream_t s; cudaEvent_t b = nullptr;
+    ProfScope(zrb_ctx* ctx, int cls, cudaStream_t stream);
+    ~ProfScope();
+};
+
+int simt_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_states* in, const zrb_states* out,
+                 float* scores, cudaStream_t s);
+int simt_backward(zrb_ctx* c, const zrb_params* p, const float* dscores, const zrb_params* g, cudaStream_t s);
+
+int tc_ctx_init(zrb_ctx* c);
+void tc_ctx_free(zrb_ctx* c);
+int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_states* in, const zrb_states* out,
+               float* scores, cudaStream_t s);
+int tc_backward(zrb_ctx* c, const zrb_params* p, const float* dscores, const zrb_params* g, cudaStream_t s);
+int tc_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, const int64_t* x, const int64_t* y,
+                        int T, int B, const zrb_states* in, const zrb_states* out, uint64_t seed, uint64_t step,
+                        float* loss, cudaStream_t s);
+int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
+              cudaStream_t s);
+
+}  // namespace zrb

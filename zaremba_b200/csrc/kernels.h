@@ -1,0 +1,48 @@
+// Internal launcher declarations (host side).  All take a cudaStream_t and return ZRB_*.
+#pragma once
+#include "common.cuh"
+
+namespace zrb {
+
+// ---- pointwise.cu -----------------------------------------------------------------------
+// out[n, :] = W[idx[n], :] * dropout   (model.py:13-14 + :105)
+int embed_dropout_fwd(const float* W, const int64_t* idx, float* out, __half* out_h, int64_t ld_h,
+                      int N, int H, int V, MaskSrc m, cudaStream_t s);
+// dW[idx[n], :] += dA[n, :] * dropout   (dW pre-zeroed)
+int embed_dropout_bwd(const float* dA, const int64_t* idx, float* dW, int N, int H, int V, MaskSrc m,
+                      cudaStream_t s);
+// pre [B,4H] holds x-part + h-part pre-activations (+bias already added); overwritten with
+// activated gates (i,f,g,o).  c_prev/c_out/h_raw/y_out [B,H]; y_out = dropout(h).
+int lstm_cell_fwd(float* pre, const float* c_prev, float* c_out, float* h_raw, float* y_out,
+                  int B, int H, int64_t elem_off, int64_t n_total, MaskSrc m, cudaStream_t s);
+// dG [B,4H] out; dc [B,H] in/out carry; dh_rec [B,H] in (may be null = 0);
+// dy_post [B,H] upstream grad on the post-dropout output
+int lstm_cell_bwd(const float* dy_post, const float* dh_rec, float* dc, const float* gates, const float* c_t,
+                  const float* c_prev, float* dG, int B, int H, int64_t elem_off, int64_t n_total, MaskSrc m,
+                  cudaStream_t s);
+// C[n, j] += bias1[j] + bias2[j]
+int add_bias2(float* C, const float* b1, const float* b2, int N, int M, cudaStream_t s);
+int add_bias1(float* C, const float* b1, int N, int M, cudaStream_t s);
+// out[j] = sum_n A[n, j]
+int colsum(const float* A, float* out, float* out2, int N, int M, cudaStream_t s);
+// softmax NLL fwd(+bwd); row_loss [N] scratch
+int softmax_nll(const float* scores, const int64_t* y, int N, int V, int B, float* row_loss, float* loss,
+                float* dscores, float* tgt_prob, cudaStream_t s);
+int dropout_mask_bytes(MaskSrc m, int64_t n, uint8_t* out, cudaStream_t s);
+
+// ---- optim.cu ----------------------------------------------------------------------------
+struct TensorList {
+    float* p[16];
+    float* g[16];
+    int64_t n[16];
+    int count;
+};
+// partials: >= 1024 floats scratch; scalars: >= 4 floats (norm, coef)
+int clip_sgd(const TensorList& tl, float lr, float max_norm, float* partials, float* scalars, float* norm_out,
+             cudaStream_t s);
+
+// ---- gemm_simt.cu ------------------------------------------------------------------------
+int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int transA, int transB, float alpha,
+             float beta, cudaStream_t s);
+
+}  // namespace zrb

@@ -1,0 +1,145 @@
+"""Fused train / eval step around `Model`: one library call per iteration of
+main.py:109-117 (zero_grad, detach, forward, nll_loss, backward, clip_grad_norm_, SGD) and
+of main.py:91-94 (perplexity's inner step), plus the data-parallel gradient all-reduce.
+
+Semantics are the reference's: the loss is summed over the batch and averaged over time
+(main.py:82-84), so data-parallel ranks SUM their gradients (one `all_reduce` of the flat
+gradient buffer) before every rank clips on the global norm and applies the same update --
+identical to a single process at `--batch_size B * world_size`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .parallel import allreduce_sum_
+from .model import Model
+
+
+def minibatch(data, batch_size, seq_length):
+    """main.py:61-74: token column -> list of (x, y) [T,B] int64 CPU views (same windows,
+    same non-contiguous layout the reference hands to the model)."""
+    data = torch.as_tensor(np.asarray(data), dtype=torch.int64).reshape(-1)
+    num_batches = data.size(0) // batch_size
+    data = data[: num_batches * batch_size].view(batch_size, -1)
+    out = []
+    width = data.size(1)
+    for i in range(0, width - 1, seq_length):
+        seqlen = min(seq_length, width - 1 - i)
+        if seqlen < width - 1 - i:
+            out.append((data[:, i:i + seqlen].transpose(1, 0), data[:, i + 1:i + seqlen + 1].transpose(1, 0)))
+    return out
+
+
+class Trainer:
+    def __init__(self, model: Model, batch_size: int, seq_length: int, process_group=None):
+        if model.lstm_type != "pytorch":
+            raise ValueError("Trainer drives the --lstm_type pytorch layout")
+        dev = model.embed.W.device
+        if dev.type != "cuda":
+            raise RuntimeError("Trainer needs the model on a CUDA device (no CPU fallback)")
+        self.model, self.B, self.T, self.dev = model, batch_size, seq_length, dev
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        params = model.ordered_parameters()
+        sizes = [p.numel() for p in params]
+        # one flat parameter buffer and one flat gradient buffer; the nn.Parameters become views
+        self.flat_p = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(params, sizes):
+                view = self.flat_p[off:off + n].view_as(p)
+                view.copy_(p)
+                p.data = view
+                p.grad = self.flat_g[off:off + n].view_as(p)
+                off += n
+        self._ps, self._keep_p = model._params_struct(params)
+        self._gs, self._keep_g = model._params_struct([p.grad for p in params])
+        self.states = model.state_init(batch_size)
+        self._st, self._keep_s = model._states_struct(self.states)
+        self.loss = torch.zeros((), device=dev)
+        self.norm = torch.zeros((), device=dev)
+        self.tgt_prob = torch.zeros(batch_size * seq_length, device=dev)
+        self._hx = torch.empty(seq_length, batch_size, dtype=torch.int64).pin_memory()
+        self._hy = torch.empty(seq_length, batch_size, dtype=torch.int64).pin_memory()
+        self._hloss = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.step = 0
+        self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self.ctx = model._context(seq_length, batch_size)
+        _lib.check(_lib.load().zrb_params_changed(self.ctx))
+
+    def reset_states(self):
+        for h, c in self.states:
+            h.zero_(); c.zero_()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    # ---- main.py:109-117 -----------------------------------------------------------------
+    def train_step(self, x, y, lr, max_norm):
+        """x, y: [T,B] int64 CUDA tensors (contiguous).  Returns (loss, norm) as 0-d CUDA
+        tensors (no host sync)."""
+        lib = _lib.load()
+        T, B = x.shape
+        _lib.check(lib.zrb_train_step_grads(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x), _lib.ptr(y),
+                                            T, B, C.byref(self._st), C.byref(self._st), self.seed, self.step,
+                                            _lib.ptr(self.loss), self._stream()))
+        if self.world > 1:
+            allreduce_sum_(self.flat_g, self.pg)
+        _lib.check(lib.zrb_train_step_update(self.ctx, C.byref(self._ps), C.byref(self._gs), float(lr),
+                                             float(max_norm), _lib.ptr(self.norm), self._stream()))
+        self.step += 1
+        return self.loss, self.norm
+
+    def train_step_host(self, x, y, lr, max_norm):
+        """x, y: [T,B] int64 CPU tensors exactly as main.py:71-72 builds them.  Copies them to
+        the device, runs the step and returns (loss, norm) as Python floats: the end-to-end
+        call (H2D and D2H inside)."""
+        lib = _lib.load()
+        T, B = x.shape
+        hx, hy = self._hx[:T, :B], self._hy[:T, :B]
+        if T != self.T or B != self.B:
+            hx = torch.empty(T, B, dtype=torch.int64).pin_memory(); hy = torch.empty_like(hx).pin_memory()
+        hx.copy_(x); hy.copy_(y)
+        if self.world == 1:
+            _lib.check(lib.zrb_train_step_host(self.ctx, C.byref(self._ps), C.byref(self._gs),
+                                               C.c_void_p(hx.data_ptr()), C.c_void_p(hy.data_ptr()), T, B,
+                                               C.byref(self._st), C.byref(self._st), self.seed, self.step,
+                                               float(lr), float(max_norm), C.c_void_p(self._hloss.data_ptr()),
+                                               C.c_void_p(self._hloss.data_ptr() + 4), self._stream()))
+            self.step += 1
+            return float(self._hloss[0]), float(self._hloss[1])
+        xd = hx.to(self.dev, non_blocking=True); yd = hy.to(self.dev, non_blocking=True)
+        loss, norm = self.train_step(xd, yd, lr, max_norm)
+        both = torch.stack([loss, norm]).cpu()
+        return float(both[0]), float(both[1])
+
+    # ---- main.py:91-94 --------------------------------------------------------------------
+    def eval_step(self, x, y, want_probs=False):
+        """Eval-mode forward + loss on device tokens; carries `self.states`.  Returns the loss
+        tensor (main.py:92) and, if asked, softmax(scores)[n, y_n] for the ensemble
+        (ensemble.py:100-106)."""
+        lib = _lib.load()
+        T, B = x.shape
+        _lib.check(lib.zrb_eval_step(self.ctx, C.byref(self._ps), _lib.ptr(x), _lib.ptr(y), T, B,
+                                     C.byref(self._st), C.byref(self._st), _lib.ptr(self.loss),
+                                     _lib.ptr(self.tgt_prob) if want_probs else None, self._stream()))
+        return (self.loss, self.tgt_prob[: T * B]) if want_probs else self.loss
+
+    def perplexity(self, batches):
+        """main.py:86-95 with the per-batch `.item()` sync removed: losses accumulate on the
+        device and are read once."""
+        self.reset_states()
+        acc = torch.zeros((), device=self.dev, dtype=torch.float64)
+        n = 0
+        for x, y in batches:
+            xd = x.to(self.dev).contiguous(); yd = y.to(self.dev).contiguous()
+            acc += self.eval_step(xd, yd).double() / x.shape[1]
+            n += 1
+        return math.exp(acc.item() / max(n, 1))
