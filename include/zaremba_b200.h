@@ -185,11 +185,13 @@ int  zrb_prof_read(zrb_ctx* ctx, float* h_ms, int64_t* h_counts);
 int  zrb_gemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K,
                   int32_t transA, int32_t transB, float alpha, float beta, void* stream);
 
-/* C[M,N] (fp32) = alpha * A[M,K] * B[N,K]^T (+ bias[N]) on tcgen05 tensor cores.
- * A, B: fp16, K contiguous, leading dimensions lda/ldb in elements (multiples of 8). */
-int  zrb_gemm_f16_tn(const void* A, int64_t lda, const void* B, int64_t ldb,
-                     float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
-                     float alpha, const float* bias, int32_t accumulate, void* stream);
+/* C[M,N] (fp32) = alpha * A * B^T (+ bias[N]) (+ C if accumulate) on tcgen05 tensor cores,
+ * fp16 operands, fp32 accumulation.  a_mn_major == 0: A is [M,K] with K contiguous (pitch lda);
+ * != 0: A is stored [K,M] with M contiguous (pitch lda).  Same for B with N.  Pitches are in
+ * elements and must be multiples of 8 (16 bytes); bases 16-byte aligned. */
+int  zrb_gemm_f16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
+                  int32_t b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                  float alpha, const float* bias, int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

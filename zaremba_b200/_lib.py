@@ -69,8 +69,8 @@ _SIGNATURES = {
     "zrb_prof_read": (C.c_int, [_vp, _vp, _vp]),
     "zrb_gemm_f32": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                C.c_float, _vp]),
-    "zrb_gemm_f16_tn": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                  C.c_float, _vp, C.c_int32, _vp]),
+    "zrb_gemm_f16": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int64, C.c_int32, _vp, C.c_int64, C.c_int32,
+                               C.c_int32, C.c_int32, C.c_float, _vp, C.c_int32, _vp]),
 }
 
 PROF_CLASSES = ["embed_fwd", "gemm_in", "rec_fwd", "proj_fwd", "softmax", "proj_bwd", "rec_bwd", "gemm_dx",

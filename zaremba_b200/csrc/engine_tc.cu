@@ -1,11 +1,222 @@
-// ZRB_ENGINE_TC placeholder (replaced by the tcgen05 engine).
+// ZRB_ENGINE_TC: every dense contraction of the path on tcgen05 tensor cores (fp16 operands,
+// fp32 accumulation in TMEM), pointwise math and state in fp32.
+//
+// fp16 images (K = contraction index):
+//   w_ih_h[l], w_hh_h[l] [4H, Hp]   read K-major by the forward GEMMs (X*W^T, h*W^T) and MN-major
+//   fc_w_h               [V,  Hp]   by the dgrads (dG*W, dS*W): one image serves both
+//   x_h[l]      [N, Hp]  dropout'ed input of layer l (x_h[L] feeds the projection); MN-major B of wgrads
+//   hprev_h[l]  [N+B,Hp] rows 0..B-1 = h entering the window, rows B.. = h_t: row block t is h_{t-1}
+//   dG_h        [N, G4p] kGradScale * dG;  dS_h [N, Vp] kGradScale * dscores
+// Gradient images are scaled by an exact power of two and unscaled by the consuming GEMM's alpha.
 #include "engine.h"
+#include "tc_kernels.h"
+
+struct zrb_tc_state {
+    int Hp = 0, G4p = 0, Vp = 0;
+    __half* w_ih_h[ZRB_MAX_LAYERS] = {};
+    __half* w_hh_h[ZRB_MAX_LAYERS] = {};
+    __half* fc_w_h = nullptr;
+    float* bsum[ZRB_MAX_LAYERS] = {};
+    __half* x_h[ZRB_MAX_LAYERS + 1] = {};
+    __half* hprev_h[ZRB_MAX_LAYERS] = {};
+    __half* dG_h = nullptr;
+    __half* dS_h = nullptr;
+    int64_t packed_version = 0;
+    std::vector<void*> allocs;
+};
+
 namespace zrb {
-int tc_ctx_init(zrb_ctx*) { set_error("tcgen05 engine not built yet"); return ZRB_E_INVALID; }
-void tc_ctx_free(zrb_ctx*) {}
-int tc_forward(zrb_ctx*, const zrb_params*, const int64_t*, const zrb_states*, const zrb_states*, float*, cudaStream_t) { return ZRB_E_INVALID; }
-int tc_backward(zrb_ctx*, const zrb_params*, const float*, const zrb_params*, cudaStream_t) { return ZRB_E_INVALID; }
-int tc_train_step_grads(zrb_ctx*, const zrb_params*, const zrb_params*, const int64_t*, const int64_t*, int, int, const zrb_states*, const zrb_states*, uint64_t, uint64_t, float*, cudaStream_t) { return ZRB_E_INVALID; }
-int tc_update(zrb_ctx*, const zrb_params*, const TensorList&, float, float, float*, cudaStream_t) { return ZRB_E_INVALID; }
+
+static int pad64(int n) { return (n + 63) / 64 * 64; }
+
+template <typename T>
+static int tc_alloc(zrb_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return ZRB_E_NOMEM;
+    }
+    cudaMemset(q, 0, bytes);
+    c->tc->allocs.push_back(q);
+    c->bytes += (int64_t)bytes;
+    *p = (T*)q;
+    return ZRB_OK;
 }
-extern "C" int zrb_gemm_f16_tn(const void*, int64_t, const void*, int64_t, float*, int64_t, int32_t, int32_t, int32_t, float, const float*, int32_t, void*) { zrb::set_error("not built"); return ZRB_E_INVALID; }
+
+int tc_ctx_init(zrb_ctx* c) {
+    int major = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+        set_error("the tcgen05 engine needs an sm_100 device (found compute capability %d.x)", major);
+        return ZRB_E_INVALID;
+    }
+    c->tc = new zrb_tc_state();
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
+    const size_t N = (size_t)c->cfg.max_seq * c->cfg.max_batch, B = c->cfg.max_batch;
+    t->Hp = pad64(H); t->G4p = pad64(4 * H); t->Vp = pad64(V);
+    for (int l = 0; l < L; ++l) {
+        ZRB_TRY(tc_alloc(c, &t->w_ih_h[l], (size_t)4 * H * t->Hp));
+        ZRB_TRY(tc_alloc(c, &t->w_hh_h[l], (size_t)4 * H * t->Hp));
+        ZRB_TRY(tc_alloc(c, &t->bsum[l], (size_t)4 * H));
+        ZRB_TRY(tc_alloc(c, &t->hprev_h[l], (N + B) * t->Hp));
+    }
+    for (int l = 0; l <= L; ++l) ZRB_TRY(tc_alloc(c, &t->x_h[l], N * t->Hp));
+    ZRB_TRY(tc_alloc(c, &t->fc_w_h, (size_t)V * t->Hp));
+    ZRB_TRY(tc_alloc(c, &t->dG_h, N * t->G4p));
+    ZRB_TRY(tc_alloc(c, &t->dS_h, N * t->Vp));
+    return ZRB_OK;
+}
+
+void tc_ctx_free(zrb_ctx* c) {
+    if (!c->tc) return;
+    for (void* p : c->tc->allocs) cudaFree(p);
+    delete c->tc;
+    c->tc = nullptr;
+}
+
+// rebuild the fp16 weight images when parameter values changed (main.py:116-117 / zrb_clip_sgd)
+static int tc_pack_weights(zrb_ctx* c, const zrb_params* p, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    if (t->packed_version == c->weights_version) return ZRB_OK;
+    ProfScope ps(c, ZRB_PROF_PACK, s);
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
+    for (int l = 0; l < L; ++l) {
+        ZRB_TRY(convert_pad_f16(p->w_ih[l], H, t->w_ih_h[l], t->Hp, 4 * H, H, 1.f, s));
+        ZRB_TRY(convert_pad_f16(p->w_hh[l], H, t->w_hh_h[l], t->Hp, 4 * H, H, 1.f, s));
+        ZRB_TRY(add_vec(p->b_ih[l], p->b_hh[l], t->bsum[l], 4 * H, s));
+    }
+    ZRB_TRY(convert_pad_f16(p->fc_w, H, t->fc_w_h, t->Hp, V, H, 1.f, s));
+    t->packed_version = c->weights_version;
+    return ZRB_OK;
+}
+
+int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_states* in, const zrb_states* out,
+               float* scores, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab, T = c->T, B = c->B, N = T * B;
+    const int Hp = t->Hp;
+    const size_t bh = (size_t)B * H * sizeof(float);
+    ZRB_TRY(tc_pack_weights(c, p, s));
+    ZRB_CUDA(cudaMemcpyAsync(c->x_saved, x, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < L; ++l) {
+        ZRB_CUDA(cudaMemcpyAsync(c->h0s[l], in->h[l], bh, cudaMemcpyDeviceToDevice, s));
+        ZRB_CUDA(cudaMemcpyAsync(c->c0s[l], in->c[l], bh, cudaMemcpyDeviceToDevice, s));
+        ZRB_TRY(convert_pad_f16(c->h0s[l], H, t->hprev_h[l], Hp, B, H, 1.f, s));
+    }
+    {
+        ProfScope ps(c, ZRB_PROF_EMBED_FWD, s);
+        ZRB_TRY(embed_dropout_fwd(p->embed_w, x, nullptr, t->x_h[0], Hp, N, H, V, site_mask(c, 0), s));
+    }
+    for (int l = 0; l < L; ++l) {
+        float* G = c->gates[l];
+        {
+            ProfScope ps(c, ZRB_PROF_GEMM_IN, s);
+            ZRB_TRY(gemm_f16_tc(t->x_h[l], Hp, 0, t->w_ih_h[l], Hp, 0, G, 4 * H, N, 4 * H, H, 1.f, t->bsum[l], 0, s));
+        }
+        MaskSrc m = site_mask(c, l + 1);
+        ProfScope ps(c, ZRB_PROF_REC_FWD, s);
+        for (int tt = 0; tt < T; ++tt) {
+            const float* c_prev = tt ? c->cst[l] + (size_t)(tt - 1) * B * H : c->c0s[l];
+            float* Gt = G + (size_t)tt * B * 4 * H;
+            ZRB_TRY(gemm_f16_tc(t->hprev_h[l] + (size_t)tt * B * Hp, Hp, 0, t->w_hh_h[l], Hp, 0, Gt, 4 * H, B, 4 * H, H,
+                                1.f, nullptr, 1, s));
+            ZRB_TRY(lstm_cell_fwd_tc(Gt, c_prev, c->cst[l] + (size_t)tt * B * H, c->hraw[l] + (size_t)tt * B * H,
+                                     t->hprev_h[l] + (size_t)(tt + 1) * B * Hp, t->x_h[l + 1] + (size_t)tt * B * Hp, Hp, B,
+                                     H, (int64_t)tt * B * H, (int64_t)N * H, m, s));
+        }
+        ZRB_CUDA(cudaMemcpyAsync(out->h[l], c->hraw[l] + (size_t)(T - 1) * B * H, bh, cudaMemcpyDeviceToDevice, s));
+        ZRB_CUDA(cudaMemcpyAsync(out->c[l], c->cst[l] + (size_t)(T - 1) * B * H, bh, cudaMemcpyDeviceToDevice, s));
+    }
+    if (scores) {
+        ProfScope ps(c, ZRB_PROF_PROJ_FWD, s);
+        ZRB_TRY(gemm_f16_tc(t->x_h[L], Hp, 0, t->fc_w_h, Hp, 0, scores, V, N, V, H, 1.f, p->fc_b, 0, s));
+    }
+    return ZRB_OK;
+}
+
+// backward from the scaled fp16 image dS_h already in place
+static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_params* g, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab, T = c->T, B = c->B, N = T * B;
+    const int Hp = t->Hp, G4p = t->G4p, Vp = t->Vp;
+    const size_t bh = (size_t)B * H;
+    const float inv = 1.f / kGradScale;
+    float* dY = c->dy;
+    float* dX = c->dx;
+    {
+        ProfScope ps(c, ZRB_PROF_PROJ_BWD, s);
+        // dA[N,H] = dS[N,V] * W[V,H]       (W image read MN-major)
+        ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 0, t->fc_w_h, Hp, 1, dY, H, N, H, V, inv, nullptr, 0, s));
+        // dW[V,H] = dS^T[V,N] * A[N,H]     (both operands MN-major: contraction over tokens)
+        ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s));
+        ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, N, V, inv, s));
+    }
+    for (int l = L - 1; l >= 0; --l) {
+        MaskSrc m = site_mask(c, l + 1);
+        ZRB_CUDA(cudaMemsetAsync(c->dc, 0, bh * sizeof(float), s));
+        {
+            ProfScope ps(c, ZRB_PROF_REC_BWD, s);
+            for (int tt = T - 1; tt >= 0; --tt) {
+                const float* c_prev = tt ? c->cst[l] + (size_t)(tt - 1) * bh : c->c0s[l];
+                ZRB_TRY(lstm_cell_bwd_tc(dY + (size_t)tt * bh, tt == T - 1 ? nullptr : c->dh_rec, c->dc,
+                                         c->gates[l] + (size_t)tt * B * 4 * H, c->cst[l] + (size_t)tt * bh, c_prev,
+                                         c->dG + (size_t)tt * B * 4 * H, t->dG_h + (size_t)tt * B * G4p, G4p, B, H,
+                                         (int64_t)tt * bh, (int64_t)N * H, m, s));
+                if (tt > 0)  // dh_{t-1}[B,H] = dG_t[B,4H] * W_hh[4H,H]
+                    ZRB_TRY(gemm_f16_tc(t->dG_h + (size_t)tt * B * G4p, G4p, 0, t->w_hh_h[l], Hp, 1, c->dh_rec, H, B, H,
+                                        4 * H, inv, nullptr, 0, s));
+            }
+        }
+        {
+            ProfScope ps(c, ZRB_PROF_GEMM_DX, s);
+            ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 0, t->w_ih_h[l], Hp, 1, dX, H, N, H, 4 * H, inv, nullptr, 0, s));
+        }
+        ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
+        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->x_h[l], Hp, 1, g->w_ih[l], H, 4 * H, H, N, inv, nullptr, 0, s));
+        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->hprev_h[l], Hp, 1, g->w_hh[l], H, 4 * H, H, N, inv, nullptr, 0, s));
+        ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
+        float* tmp = dY; dY = dX; dX = tmp;
+    }
+    ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);
+    ZRB_CUDA(cudaMemsetAsync(g->embed_w, 0, (size_t)V * H * sizeof(float), s));
+    ZRB_TRY(embed_dropout_bwd(dY, c->x_saved, g->embed_w, N, H, V, site_mask(c, 0), s));
+    return ZRB_OK;
+}
+
+int tc_backward(zrb_ctx* c, const zrb_params* p, const float* dscores, const zrb_params* g, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int N = c->T * c->B, V = c->cfg.vocab;
+    ZRB_TRY(convert_pad_f16(dscores, V, t->dS_h, t->Vp, N, V, kGradScale, s));
+    return tc_backward_from_image(c, p, g, s);
+}
+
+int tc_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, const int64_t* x, const int64_t* y,
+                        int T, int B, const zrb_states* in, const zrb_states* out, uint64_t seed, uint64_t step,
+                        float* loss, cudaStream_t s) {
+    c->T = T; c->B = B; c->train = 1; c->seed = seed; c->step = step;
+    c->have_fwd = false;
+    ZRB_TRY(tc_forward(c, p, x, in, out, c->scores, s));
+    c->have_fwd = true;
+    {
+        ProfScope ps(c, ZRB_PROF_SOFTMAX, s);
+        ZRB_TRY(softmax_nll(c->scores, y, T * B, c->cfg.vocab, B, c->row_loss, loss, nullptr, nullptr, s, c->tc->dS_h,
+                            c->tc->Vp, kGradScale));
+    }
+    return tc_backward_from_image(c, p, g, s);
+}
+
+int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
+              cudaStream_t s) {
+    {
+        ProfScope ps(c, ZRB_PROF_CLIP_SGD, s);
+        ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, s));
+    }
+    c->weights_version++;
+    return ZRB_OK;
+}
+
+}  // namespace zrb

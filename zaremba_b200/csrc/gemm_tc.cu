@@ -1,0 +1,289 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:
+//     C[M,N] (fp32) = alpha * A * B^T (+ bias[N]) (+ C)
+// A is [M,K] (K-major) or stored [K,M] (MN-major); B is [N,K] (K-major) or stored [K,N]
+// (MN-major).  fp16 operands, fp32 accumulation in TMEM.
+//
+//   warp 0   TMA producer   : cp.async.bulk.tensor 2-D boxes, 128B swizzle, 6-stage mbarrier ring
+//   warp 1   MMA issuer     : one thread issues tcgen05.mma 128x128x16 (cta_group::1), commits
+//                             to the ring's "empty" barriers and to the accumulator "full" barrier
+//   warp 2   TMEM allocator : 256 columns = two 128x128 fp32 accumulators (epilogue of tile i
+//                             overlaps the MMAs of tile i+1)
+//   warps 4-7 epilogue      : tcgen05.ld 32x32b, alpha/bias, fp32 stores
+//
+// Every batched contraction of the path runs here: X*W_ih^T, the vocabulary projection, their
+// dgrads (weights read MN-major from the same fp16 image, no transposed copies) and the
+// wgrads (both operands MN-major: contraction over tokens).  Roofline: tensor pipe
+// (2*M*N*K flop per call); operands stream once from HBM/L2 via TMA.
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "tc_host.h"
+
+namespace zrb {
+
+using namespace tc;
+
+constexpr int GBM = 128, GBN = 128, GBK = 64;
+constexpr int kStages = 6, kAccStages = 2;
+constexpr int kABytes = GBM * GBK * 2, kBBytes = GBN * GBK * 2;
+constexpr int kGemmSmem = kStages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kGemmThreads = 256;
+
+struct GemmArgs {
+    int M, N, K;
+    float alpha;
+    const float* bias;
+    float* C;
+    int64_t ldc;
+    int accumulate;
+    int tiles_m, tiles_n;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + kStages * kABytes;
+    uint64_t* bars = (uint64_t*)(smem + kStages * (kABytes + kBBytes));
+    uint64_t* full = bars;                       // [kStages]
+    uint64_t* empty = bars + kStages;            // [kStages]
+    uint64_t* acc_full = bars + 2 * kStages;     // [kAccStages]
+    uint64_t* acc_empty = acc_full + kAccStages; // [kAccStages]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_kb = (p.K + GBK - 1) / GBK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<kAccStages * GBN>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile % p.tiles_m) * GBM, n0 = (tile / p.tiles_m) * GBN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], kABytes + kBBytes);
+                uint8_t* a = sA + s * kABytes;
+                uint8_t* b = sB + s * kBBytes;
+                if (!A_MN) {
+                    tma_load_2d(a, &tma_a, &full[s], kb * GBK, m0);
+                } else {
+                    tma_load_2d(a, &tma_a, &full[s], m0, kb * GBK);
+                    tma_load_2d(a + kABytes / 2, &tma_a, &full[s], m0 + 64, kb * GBK);
+                }
+                if (!B_MN) {
+                    tma_load_2d(b, &tma_b, &full[s], kb * GBK, n0);
+                } else {
+                    tma_load_2d(b, &tma_b, &full[s], n0, kb * GBK);
+                    tma_load_2d(b + kBBytes / 2, &tma_b, &full[s], n0 + 64, kb * GBK);
+                }
+                if (++s == kStages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_f16(GBM, GBN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&acc_empty[as], aph ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + as * GBN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * kABytes), b_addr = smem_u32(sB + s * kBBytes);
+#pragma unroll
+                for (int k = 0; k < GBK / 16; ++k) {
+                    // K-major, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart, +32 B per K=16 step.
+                    // MN-major, 128B swizzle: 64-element column blocks (BK*128 B apart = LBO), 8 k-rows per
+                    // 1024 B group (SBO), +16 k-rows = 2048 B per step.
+                    uint64_t da = A_MN ? make_smem_desc(a_addr + k * 2048, kABytes / 2, 1024, kSwizzle128B)
+                                       : make_smem_desc(a_addr + k * 32, 16, 1024, kSwizzle128B);
+                    uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, kBBytes / 2, 1024, kSwizzle128B)
+                                       : make_smem_desc(b_addr + k * 32, 16, 1024, kSwizzle128B);
+                    umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);
+                if (++s == kStages) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&acc_full[as]);
+            if (++as == kAccStages) { as = 0; aph ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;  // TMEM lanes [32q, 32q+32)
+        int as = 0; uint32_t aph = 0;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((((uintptr_t)p.C) & 15) == 0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile % p.tiles_m) * GBM, n0 = (tile / p.tiles_m) * GBN;
+            mbar_wait(&acc_full[as], aph);
+            tcgen05_fence_after();
+            const int row = m0 + q * 32 + lane;
+            float* crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll 1
+            for (int c = 0; c < GBN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * GBN + c * 32, v);
+                tmem_ld_wait();
+                const int nb = n0 + c * 32;
+                if (row < p.M && nb < p.N) {
+                    if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o;
+                            o.x = p.alpha * __uint_as_float(v[j]);
+                            o.y = p.alpha * __uint_as_float(v[j + 1]);
+                            o.z = p.alpha * __uint_as_float(v[j + 2]);
+                            o.w = p.alpha * __uint_as_float(v[j + 3]);
+                            if (p.bias) {
+                                float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + j);
+                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            }
+                            float4* dst = reinterpret_cast<float4*>(crow + nb + j);
+                            if (p.accumulate) {
+                                float4 old = *dst;
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *dst = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (nb + j < p.N) {
+                                float o = p.alpha * __uint_as_float(v[j]);
+                                if (p.bias) o += p.bias[nb + j];
+                                if (p.accumulate) o += crow[nb + j];
+                                crow[nb + j] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (++as == kAccStages) { as = 0; aph ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 2) tmem_dealloc<kAccStages * GBN>(tmem_base);
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int g_num_sms = 0;
+bool g_attr_set[4] = {false, false, false, false};
+
+}  // namespace
+
+int tc_num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// fp16 2-D tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements
+int tc_make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                     uint32_t box_outer, int swizzle128) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return ZRB_E_CUDA;
+    }
+    ZRB_REQUIRE((ld * 2) % 16 == 0 && (((uintptr_t)ptr) & 15) == 0, "TMA operand needs 16-byte aligned base and pitch");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", (int)r,
+                  (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+        return ZRB_E_CUDA;
+    }
+    return ZRB_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
+    auto kern = gemm_f16_tc_kernel<A_MN, B_MN>;
+    const int idx = (A_MN ? 2 : 0) + (B_MN ? 1 : 0);
+    if (!g_attr_set[idx]) {
+        ZRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        g_attr_set[idx] = true;
+    }
+    int grid = a.tiles_m * a.tiles_n;
+    if (grid > tc_num_sms()) grid = tc_num_sms();
+    kern<<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, a);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t ldb, int b_mn, float* C, int64_t ldc,
+                int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s) {
+    if (M <= 0 || N <= 0) return ZRB_OK;
+    ZRB_REQUIRE(K > 0, "gemm_f16_tc needs K > 0");
+    CUtensorMap ta, tb;
+    if (!a_mn) ZRB_TRY(tc_make_tmap_f16(&ta, A, K, M, lda, GBK, GBM, 1));
+    else       ZRB_TRY(tc_make_tmap_f16(&ta, A, M, K, lda, 64, GBK, 1));
+    if (!b_mn) ZRB_TRY(tc_make_tmap_f16(&tb, B, K, N, ldb, GBK, GBN, 1));
+    else       ZRB_TRY(tc_make_tmap_f16(&tb, B, N, K, ldb, 64, GBK, 1));
+    GemmArgs a;
+    a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.bias = bias; a.C = C; a.ldc = ldc; a.accumulate = accumulate;
+    a.tiles_m = cdiv(M, GBM); a.tiles_n = cdiv(N, GBN);
+    if (!a_mn && !b_mn) return launch_gemm<false, false>(ta, tb, a, s);
+    if (!a_mn && b_mn) return launch_gemm<false, true>(ta, tb, a, s);
+    if (a_mn && !b_mn) return launch_gemm<true, false>(ta, tb, a, s);
+    return launch_gemm<true, true>(ta, tb, a, s);
+}
+
+}  // namespace zrb
+
+extern "C" int zrb_gemm_f16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
+                            int32_t b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha,
+                            const float* bias, int32_t accumulate, void* stream) {
+    ZRB_REQUIRE(A && B && C, "null argument");
+    return zrb::gemm_f16_tc((const __half*)A, lda, a_mn_major, (const __half*)B, ldb, b_mn_major, C, ldc, M, N, K,
+                            alpha, bias, accumulate, (cudaStream_t)stream);
+}

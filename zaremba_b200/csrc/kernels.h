@@ -26,8 +26,10 @@ int add_bias1(float* C, const float* b1, int N, int M, cudaStream_t s);
 // out[j] = sum_n A[n, j]
 int colsum(const float* A, float* out, float* out2, int N, int M, cudaStream_t s);
 // softmax NLL fwd(+bwd); row_loss [N] scratch
+// optional ds_h: scaled fp16 image of the gradient (pitch ld_s) for the tensor-core engine
 int softmax_nll(const float* scores, const int64_t* y, int N, int V, int B, float* row_loss, float* loss,
-                float* dscores, float* tgt_prob, cudaStream_t s);
+                float* dscores, float* tgt_prob, cudaStream_t s, __half* ds_h = nullptr, int64_t ld_s = 0,
+                float h_scale = 1.f);
 int dropout_mask_bytes(MaskSrc m, int64_t n, uint8_t* out, cudaStream_t s);
 
 // ---- optim.cu ----------------------------------------------------------------------------

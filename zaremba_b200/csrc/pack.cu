@@ -1,0 +1,65 @@
+// fp32 -> fp16 image builders for the tcgen05 engine (HBM-bound streaming kernels).
+#include "kernels.h"
+#include "tc_kernels.h"
+
+namespace zrb {
+
+// dst[r, 0..cols) = half(scale * src[r, 0..cols)), dst pitch ld_dst (>= cols), pad columns zeroed
+__global__ void convert_pad_kernel(const float* __restrict__ src, int64_t ld_src, __half* __restrict__ dst,
+                                   int64_t ld_dst, int rows, int cols, float scale) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)rows * ld_dst;
+    for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
+        float v = c < cols ? src[(int64_t)r * ld_src + c] * scale : 0.f;
+        v = fminf(fmaxf(v, -65504.f), 65504.f);
+        dst[i] = __float2half_rn(v);
+    }
+}
+
+int convert_pad_f16(const float* src, int64_t ld_src, __half* dst, int64_t ld_dst, int rows, int cols, float scale,
+                    cudaStream_t s) {
+    int64_t total = (int64_t)rows * ld_dst;
+    if (!total) return ZRB_OK;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    convert_pad_kernel<<<blocks, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols, scale);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s) {
+    add_vec_kernel<<<cdiv(n, 256), 256, 0, s>>>(a, b, out, n);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+// out[j] = inv_scale * sum_n A[n, j]  for an fp16 matrix with pitch ld
+__global__ void colsum_h_kernel(const __half* __restrict__ A, int64_t ld, float* __restrict__ out, int N, int M,
+                                float inv_scale) {
+    __shared__ float part[8][33];
+    int col = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (col < M)
+        for (int n = threadIdx.y; n < N; n += 8) acc += __half2float(A[(int64_t)n * ld + col]);
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < M) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += part[r][threadIdx.x];
+        out[col] = t * inv_scale;
+    }
+}
+int colsum_h(const __half* A, int64_t ld, float* out, int N, int M, float inv_scale, cudaStream_t s) {
+    dim3 blk(32, 8);
+    colsum_h_kernel<<<cdiv(M, 32), blk, 0, s>>>(A, ld, out, N, M, inv_scale);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+}  // namespace zrb

@@ -201,7 +201,8 @@ int colsum(const float* A, float* out, float* out2, int N, int M, cudaStream_t s
 // ----------------------------------------------------------------------------------------
 __global__ void softmax_nll_kernel(const float* __restrict__ scores, const int64_t* __restrict__ y, int N, int V,
                                    float gscale, float* __restrict__ row_loss, float* __restrict__ dscores,
-                                   float* __restrict__ tgt_prob) {
+                                   float* __restrict__ tgt_prob, __half* __restrict__ ds_h, int64_t ld_s,
+                                   float h_scale) {
     __shared__ float s_m[32], s_s[32];
     int n = blockIdx.x;
     const float* row = scores + (int64_t)n * V;
@@ -248,12 +249,15 @@ __global__ void softmax_nll_kernel(const float* __restrict__ scores, const int64
         row_loss[n] = -(zt - mx - logf(sum));
         if (tgt_prob) tgt_prob[n] = expf(zt - mx) * inv;
     }
-    if (dscores) {
-        float* drow = dscores + (int64_t)n * V;
+    if (dscores || ds_h) {
+        float* drow = dscores ? dscores + (int64_t)n * V : nullptr;
+        __half* hrow = ds_h ? ds_h + (int64_t)n * ld_s : nullptr;
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
             float p = __expf(row[v] - mx) * inv;
             if (v == tgt) p -= 1.f;
-            drow[v] = p * gscale;
+            p *= gscale;
+            if (drow) drow[v] = p;
+            if (hrow) hrow[v] = __float2half_rn(fminf(fmaxf(p * h_scale, -65504.f), 65504.f));
         }
     }
 }
@@ -274,10 +278,10 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int N, fl
 }
 
 int softmax_nll(const float* scores, const int64_t* y, int N, int V, int B, float* row_loss, float* loss,
-                float* dscores, float* tgt_prob, cudaStream_t s) {
+                float* dscores, float* tgt_prob, cudaStream_t s, __half* ds_h, int64_t ld_s, float h_scale) {
     if (N == 0) return ZRB_OK;
     float gscale = (float)((double)B / (double)N);
-    softmax_nll_kernel<<<N, 512, 0, s>>>(scores, y, N, V, gscale, row_loss, dscores, tgt_prob);
+    softmax_nll_kernel<<<N, 512, 0, s>>>(scores, y, N, V, gscale, row_loss, dscores, tgt_prob, ds_h, ld_s, h_scale);
     ZRB_KERNEL_CHECK();
     if (loss) {
         loss_reduce_kernel<<<1, 256, 0, s>>>(row_loss, N, gscale, loss);
