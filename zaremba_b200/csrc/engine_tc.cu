@@ -9,6 +9,9 @@
 //   dG_h        [N, G4p] kGradScale * dG;  dS_h [N, Vp] kGradScale * dscores
 // Gradient images are scaled by an exact power of two and unscaled by the consuming GEMM's alpha.
 #include "engine.h"
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_kernels.h"
 
 struct zrb_tc_state {
@@ -23,6 +26,14 @@ struct zrb_tc_state {
     __half* dS_h = nullptr;
     int64_t packed_version = 0;
     std::vector<void*> allocs;
+    // persistent recurrence
+    zrb::RecPlan fplan{};
+    __half* w_img_f[ZRB_MAX_LAYERS] = {};
+    __half* h_img = nullptr;
+    unsigned int* counter = nullptr;
+    zrb::RecPlan bplan{};
+    __half* w_img_b[ZRB_MAX_LAYERS] = {};
+    __half* g_img = nullptr;
 };
 
 namespace zrb {
@@ -68,6 +79,22 @@ int tc_ctx_init(zrb_ctx* c) {
     ZRB_TRY(tc_alloc(c, &t->fc_w_h, (size_t)V * t->Hp));
     ZRB_TRY(tc_alloc(c, &t->dG_h, N * t->G4p));
     ZRB_TRY(tc_alloc(c, &t->dS_h, N * t->Vp));
+    ZRB_TRY(rec_fwd_plan(H, c->cfg.max_batch, &t->fplan));
+    const char* force = getenv("ZRB_REC");
+    if (force && !strcmp(force, "steps")) t->fplan.ok = 0;   // A/B switch: per-timestep launches
+    if (t->fplan.ok) {
+        const RecPlan& fp = t->fplan;
+        for (int l = 0; l < L; ++l) ZRB_TRY(tc_alloc(c, &t->w_img_f[l], (size_t)fp.nCTA * fp.Kc * fp.G * 64));
+        ZRB_TRY(tc_alloc(c, &t->h_img, (size_t)(c->cfg.max_seq + 1) * fp.Kc * fp.GB * 64));
+        ZRB_TRY(tc_alloc(c, &t->counter, 64));
+    }
+    ZRB_TRY(rec_bwd_plan(H, c->cfg.max_batch, &t->bplan));
+    if (!t->fplan.ok || (force && !strcmp(force, "fwdonly"))) t->bplan.ok = 0;
+    if (t->bplan.ok) {
+        const RecPlan& bp = t->bplan;
+        for (int l = 0; l < L; ++l) ZRB_TRY(tc_alloc(c, &t->w_img_b[l], (size_t)bp.nCTA * bp.Kc * bp.G * 64));
+        ZRB_TRY(tc_alloc(c, &t->g_img, (size_t)2 * 4 * bp.Kc * bp.GB * 64));
+    }
     return ZRB_OK;
 }
 
@@ -88,6 +115,8 @@ static int tc_pack_weights(zrb_ctx* c, const zrb_params* p, cudaStream_t s) {
         ZRB_TRY(convert_pad_f16(p->w_ih[l], H, t->w_ih_h[l], t->Hp, 4 * H, H, 1.f, s));
         ZRB_TRY(convert_pad_f16(p->w_hh[l], H, t->w_hh_h[l], t->Hp, 4 * H, H, 1.f, s));
         ZRB_TRY(add_vec(p->b_ih[l], p->b_hh[l], t->bsum[l], 4 * H, s));
+        if (t->fplan.ok) ZRB_TRY(pack_whh_fwd(p->w_hh[l], t->w_img_f[l], H, t->fplan, s));
+        if (t->bplan.ok) ZRB_TRY(pack_whh_bwd(p->w_hh[l], t->w_img_b[l], H, t->bplan, s));
     }
     ZRB_TRY(convert_pad_f16(p->fc_w, H, t->fc_w_h, t->Hp, V, H, 1.f, s));
     t->packed_version = c->weights_version;
@@ -119,6 +148,12 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
         }
         MaskSrc m = site_mask(c, l + 1);
         ProfScope ps(c, ZRB_PROF_REC_FWD, s);
+        if (t->fplan.ok) {
+            ZRB_TRY(pack_h_image(c->h0s[l], t->h_img, B, H, t->fplan, s));
+            ZRB_TRY(lstm_rec_fwd(t->fplan, t->w_img_f[l], t->h_img, G, c->c0s[l], c->cst[l], out->h[l], out->c[l],
+                                 t->hprev_h[l], t->x_h[l + 1], t->counter, T, B, H, Hp, m, s));
+            continue;
+        }
         for (int tt = 0; tt < T; ++tt) {
             const float* c_prev = tt ? c->cst[l] + (size_t)(tt - 1) * B * H : c->c0s[l];
             float* Gt = G + (size_t)tt * B * 4 * H;
@@ -153,12 +188,16 @@ static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_par
         ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 0, t->fc_w_h, Hp, 1, dY, H, N, H, V, inv, nullptr, 0, s));
         // dW[V,H] = dS^T[V,N] * A[N,H]     (both operands MN-major: contraction over tokens)
         ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s));
-        ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, N, V, inv, s));
+        ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, nullptr, N, V, inv, s));
     }
     for (int l = L - 1; l >= 0; --l) {
         MaskSrc m = site_mask(c, l + 1);
         ZRB_CUDA(cudaMemsetAsync(c->dc, 0, bh * sizeof(float), s));
-        {
+        if (t->bplan.ok) {
+            ProfScope ps(c, ZRB_PROF_REC_BWD, s);
+            ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], t->dG_h,
+                                 t->counter, T, B, H, G4p, m, s));
+        } else {
             ProfScope ps(c, ZRB_PROF_REC_BWD, s);
             for (int tt = T - 1; tt >= 0; --tt) {
                 const float* c_prev = tt ? c->cst[l] + (size_t)(tt - 1) * bh : c->c0s[l];
@@ -178,7 +217,8 @@ static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_par
         ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
         ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->x_h[l], Hp, 1, g->w_ih[l], H, 4 * H, H, N, inv, nullptr, 0, s));
         ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->hprev_h[l], Hp, 1, g->w_hh[l], H, 4 * H, H, N, inv, nullptr, 0, s));
-        ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
+        if (t->bplan.ok) ZRB_TRY(colsum_h(t->dG_h, G4p, g->b_ih[l], g->b_hh[l], N, 4 * H, inv, s));
+        else ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
         float* tmp = dY; dY = dX; dX = tmp;
     }
     ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);

@@ -1,0 +1,347 @@
+// Persistent LSTM recurrence, backward, one launch per layer (sm_100a, clusters of 4 CTAs).
+//
+//   for t in T-1..0:  dh_t = mask * dY_t + dG_{t+1} * W_hh ;  cell backward -> dG_t, dc      
+//
+// The contraction dG_{t+1}[B,4H] * W_hh[4H,H] runs over the 4H gate rows.  A CTA that owned only a few
+// hidden units would fill 16 of the 64 rows of the smallest tcgen05 tile, so instead a CLUSTER of four
+// CTAs owns UC = 4U units and splits the contraction by gate: CTA rank r holds the fp16 slice
+// W_hh[r*H:(r+1)*H, units]^T  (UC x H, K-major, canonical no-swizzle UMMA layout) resident in shared
+// memory and multiplies it with gate r's block of dG_{t+1}.  The four partial products D_r[UC x B]
+// are exchanged through distributed shared memory: every CTA stages its accumulator in its own
+// shared memory, signals the other three through a cluster-scope mbarrier, and then sums the four
+// partials for the U units whose cell math it owns (reduce-scatter over DSMEM).  dc lives in
+// registers for the whole window.
+//
+// Per step and CTA: one 72 KB bulk copy (gate r's dG image), H/16 tcgen05.mma (M=64, N=pad8(B), K=16),
+// a 4-way DSMEM reduction of U*B floats, U*B cell updates, one grid-barrier arrival.
+// Roofline: latency / shared-memory bound like the forward kernel; flops per layer call 8*T*B*H^2.
+#include "rec_common.cuh"
+
+namespace zrb {
+
+struct RecBwdArgs {
+    const __half* w_img;      // [nCluster][4][Kc][G][8][8]
+    __half* g_img;            // [2][4][Kc][GB][8][8] ring: slot (t & 1) holds kGradScale * dG_t per gate
+    const float* dy;          // [N,H] grad wrt the layer's dropout'ed output
+    const float* gates;       // [N,4H] activated (i,f,g,o)
+    const float* cst;         // [N,H]
+    const float* c0;          // [B,H]
+    __half* dG_h;             // [N,G4p] row-major, kGradScale * dG
+    unsigned int* counter;
+    int T, B, H, G4p, U, G, GB, Kc, nCTA;
+    MaskSrc m;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int a_bytes = a.Kc * a.G * 128;
+    const int b_bytes = a.Kc * a.GB * 128;
+    const int Bp = a.GB * 8;
+    const int ldd = Bp + 1;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + a_bytes;
+    float* sD = (float*)(sB + b_bytes);  // [64][Bp+1] this CTA's partial product
+    uint64_t* bars = (uint64_t*)((uint8_t*)sD + 64 * ldd * 4);
+    uint64_t* bar_a = bars;
+    uint64_t* bar_b = bars + 1;
+    uint64_t* bar_mma = bars + 2;
+    uint64_t* bar_part = bars + 3;  // 4 arrivals per step: every CTA of the cluster staged its partial
+    uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster = blockIdx.x >> 2;
+    const int UC = 4 * a.U;
+    const int jc0 = cluster * UC;            // first unit of the cluster
+    const int j0 = jc0 + (int)rank * a.U;    // first unit whose cell math this CTA owns
+    const int nu = max(0, min(a.U, a.H - j0));
+    const int T = a.T, B = a.B, H = a.H;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1); mbar_init(bar_b, 1); mbar_init(bar_mma, 1); mbar_init(bar_part, 4);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc<32>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive
+
+    if (warp == 5 && lane == 0) {
+        // ===================== loader =====================
+        const uint8_t* src = (const uint8_t*)a.w_img + ((size_t)cluster * 4 + rank) * a_bytes;
+        mbar_expect_tx(bar_a, a_bytes);
+        for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
+        for (int s = 1; s < T; ++s) {
+            const int t = T - 1 - s;                      // step being computed; needs dG_{t+1}
+            grid_counter_wait(a.counter, (unsigned int)s * a.nCTA);
+            fence_proxy_async_all();
+            mbar_expect_tx(bar_b, b_bytes);
+            const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + rank) * b_bytes;
+            bulk_load_1d(sB, img, b_bytes, bar_b);
+        }
+    } else if (warp == 4 && lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_f16(64, Bp, 0, 0);
+        const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+        const uint32_t lbo_a = a.G * 128, lbo_b = a.GB * 128;
+        bounded_mbar_wait(bar_a, 0);
+        for (int s = 1; s < T; ++s) {
+            bounded_mbar_wait(bar_b, (s - 1) & 1);
+            tcgen05_fence_after();
+            const int ksteps = a.Kc / 2;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
+                uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
+                umma_f16(tmem_d, da, db, idesc, ks != 0 ? 1u : 0u);
+            }
+            umma_commit(bar_mma);
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue: 128 threads, cells (u, b) of this CTA's U units =====================
+        const int tid = threadIdx.x;                   // 0..127
+        const int cells = a.U * Bp;
+        constexpr int kMaxCell = 4;                    // U <= 16, Bp <= 32 -> <= 512 cells / 128 threads
+        float dcreg[kMaxCell];
+#pragma unroll
+        for (int k = 0; k < kMaxCell; ++k) dcreg[k] = 0.f;
+        const uint64_t n_total = (uint64_t)T * B * H;
+        const uint32_t sD_addr = smem_u32(sD);
+        uint32_t part_addr[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) part_addr[rr] = mapa_shared(sD_addr, rr);
+        const uint32_t bar_part_addr = smem_u32(bar_part);
+        const float inv = 1.f / kGradScale;
+
+        for (int s = 0; s < T; ++s) {
+            const int t = T - 1 - s;
+            // prefetch this step's saved activations and upstream gradient
+            float gi[kMaxCell], gf[kMaxCell], gg[kMaxCell], go[kMaxCell], ct[kMaxCell], cp[kMaxCell], dyv[kMaxCell];
+#pragma unroll
+            for (int k = 0; k < kMaxCell; ++k) {
+                int cell = tid + 128 * k;
+                int u = cell / Bp, b = cell % Bp;
+                bool ok = cell < cells && u < nu && b < B;
+                gi[k] = gf[k] = gg[k] = go[k] = ct[k] = cp[k] = dyv[k] = 0.f;
+                if (ok) {
+                    const int j = j0 + u;
+                    const size_t n = (size_t)t * B + b;
+                    const float* grow = a.gates + n * 4 * H + j;
+                    gi[k] = __ldg(grow); gf[k] = __ldg(grow + H); gg[k] = __ldg(grow + 2 * (size_t)H);
+                    go[k] = __ldg(grow + 3 * (size_t)H);
+                    ct[k] = __ldg(a.cst + n * H + j);
+                    cp[k] = t > 0 ? __ldg(a.cst + (n - B) * H + j) : __ldg(a.c0 + (size_t)b * H + j);
+                    dyv[k] = __ldg(a.dy + n * H + j) * mask_mul1(a.m, (uint64_t)n * H + j, n_total);
+                }
+            }
+            if (s > 0) {
+                bounded_mbar_wait(bar_mma, (s - 1) & 1);
+                tcgen05_fence_after();
+                // TMEM -> own shared staging: accumulator row i (cluster-local unit) in lane (i%16)+32*(i/16)
+                for (int c0 = 0; c0 < Bp; c0 += 8) {
+                    uint32_t v[8];
+                    tmem_ld_32x8(tmem_d + ((uint32_t)(32 * warp) << 16) + c0, v);
+                    tmem_ld_wait();
+                    if (lane < 16) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) sD[(16 * warp + lane) * ldd + c0 + i] = __uint_as_float(v[i]);
+                    }
+                }
+                tcgen05_fence_before();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
+                {   // wait until all four CTAs of the cluster staged their partials
+                    uint32_t n = 0; long long t0 = 0;
+                    while (!mbar_try_wait_acq_cluster(bar_part, (s - 1) & 1)) {
+                        if ((++n & 0xFFFu) == 0) {
+                            long long now = clock64();
+                            if (t0 == 0) t0 = now;
+                            else if (now - t0 > kSpinCycles) asm volatile("trap;");
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxCell; ++k) {
+                int cell = tid + 128 * k;
+                int u = cell / Bp, b = cell % Bp;
+                bool ok = cell < cells && u < nu && b < B;
+                if (!ok) continue;
+                float dh = dyv[k];
+                if (s > 0) {
+                    const uint32_t off = (uint32_t)(((int)rank * a.U + u) * ldd + b) * 4u;
+                    float r = ld_dsmem_f32(part_addr[0] + off) + ld_dsmem_f32(part_addr[1] + off) +
+                              ld_dsmem_f32(part_addr[2] + off) + ld_dsmem_f32(part_addr[3] + off);
+                    dh += r * inv;
+                }
+                const float tc = tanhf(ct[k]);
+                const float d_o = dh * tc;
+                const float dcc = dcreg[k] + dh * go[k] * (1.f - tc * tc);
+                const float d_i = dcc * gg[k], d_g = dcc * gi[k], d_f = dcc * cp[k];
+                dcreg[k] = dcc * gf[k];
+                float dg4[4];
+                dg4[0] = d_i * gi[k] * (1.f - gi[k]);
+                dg4[1] = d_f * gf[k] * (1.f - gf[k]);
+                dg4[2] = d_g * (1.f - gg[k] * gg[k]);
+                dg4[3] = d_o * go[k] * (1.f - go[k]);
+                const int j = j0 + u;
+                const size_t n = (size_t)t * B + b;
+                __half* hrow = a.dG_h + n * a.G4p + j;
+                __half* img = a.g_img + (size_t)(t & 1) * 4 * ((size_t)a.Kc * a.GB * 64) +
+                              ((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = fminf(fmaxf(dg4[q] * kGradScale, -65504.f), 65504.f);
+                    __half hv = __float2half_rn(v);
+                    hrow[(size_t)q * H] = hv;
+                    img[(size_t)q * ((size_t)a.Kc * a.GB * 64)] = hv;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0) {
+                __threadfence();
+                fence_proxy_async_all();
+                atomicAdd(a.counter, 1u);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 4) tmem_dealloc<32>(tmem_d);
+    cluster_sync_all();   // no CTA leaves while a peer may still read its staged partial
+}
+
+// w_img[cluster][r][kc][g][rr][e] = half(W_hh[r*H + kc*8+e, cluster*UC + g*8+rr]): one warp per (cluster, r, kc)
+// reads 8 rows x UC contiguous floats and writes one contiguous 16*UC-byte block.
+__global__ void pack_whh_bwd_kernel(const float* __restrict__ W, __half* __restrict__ img, int H, int UC, int G, int Kc,
+                                    int nCluster) {
+    __shared__ __half tile[8][8 * 64];
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)nCluster * 4 * Kc;
+    for (long long w = (long long)blockIdx.x * 8 + warp_in_block; w < total; w += (long long)gridDim.x * 8) {
+        const int kc = (int)(w % Kc);
+        const int r = (int)((w / Kc) & 3);
+        const int cl = (int)(w / ((long long)Kc * 4));
+        __half* t = tile[warp_in_block];
+        const int rows8 = G * 8;
+        for (int idx = lane; idx < 8 * rows8; idx += 32) {
+            int e = idx / rows8, u = idx % rows8;            // u fastest: contiguous global reads
+            int k = kc * 8 + e, j = cl * UC + u;
+            float v = (k < H && u < UC && j < H) ? W[((size_t)r * H + k) * H + j] : 0.f;
+            t[u * 8 + e] = __float2half_rn(v);
+        }
+        __syncwarp();
+        __half* dst = img + (((size_t)cl * 4 + r) * Kc + kc) * ((size_t)G * 64);
+        for (int idx = lane; idx < rows8 * 8; idx += 32) dst[idx] = t[idx];
+        __syncwarp();
+    }
+}
+
+int rec_bwd_plan(int H, int B, RecPlan* plan) {
+    int nsm = tc_num_sms();
+    int Kp = (H + 15) / 16 * 16;
+    plan->Kc = Kp / 8;
+    plan->GB = (B + 7) / 8;
+    plan->ok = 0;
+    if (plan->GB * 8 > 32) return ZRB_OK;
+    int max_clusters = (nsm - 16) / 4;   // clusters of 4 strand up to 16 SMs (GPC remainders)
+    for (int U = 16; U >= 1; --U) {
+        int UC = 4 * U;
+        if (UC % 8) continue;
+        int ncl = (H + UC - 1) / UC;
+        if (ncl > max_clusters) break;
+        int G = UC / 8;
+        size_t smem = (size_t)plan->Kc * G * 128 + (size_t)plan->Kc * plan->GB * 128 + 64 * (plan->GB * 8 + 1) * 4 +
+                      64 + 256;
+        if (smem <= 227 * 1024) {
+            plan->U = U; plan->G = G; plan->nCTA = ncl * 4; plan->smem = (int)smem; plan->ok = 1;
+            return ZRB_OK;
+        }
+    }
+    return ZRB_OK;
+}
+
+int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s) {
+    pack_whh_bwd_kernel<<<148 * 4, 256, 0, s>>>(W, img, H, 4 * p.U, p.G, p.Kc, p.nCTA / 4);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
+                 const float* cst, const float* c0, __half* dG_h, unsigned int* counter, int T, int B, int H, int G4p,
+                 MaskSrc m, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    ZRB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+    RecBwdArgs a;
+    a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
+    a.counter = counter;
+    a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.nCTA);
+    cfg.blockDim = dim3(kRecThreads);
+    cfg.dynamicSmemBytes = (size_t)p.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
+    if (e != cudaSuccess) {
+        // some drivers refuse cooperative + cluster together: the grid (<= 132 CTAs, one per SM) is
+        // co-resident on an otherwise idle device anyway
+        (void)cudaGetLastError();
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
+    }
+    if (e != cudaSuccess) {
+        set_error("lstm_rec_bwd launch failed: %s", cudaGetErrorString(e));
+        return ZRB_E_CUDA;
+    }
+    count_launch();
+    return ZRB_OK;
+}
+
+}  // namespace zrb

@@ -1,0 +1,285 @@
+// Persistent LSTM recurrence, forward, one launch per layer (sm_100a, cooperative launch).
+//
+//   for t in 0..T-1:   gates_t = XG_t + h_{t-1} * W_hh^T ;  (i,f,g,o) ;  c_t, h_t     (model.py:34-45)
+//
+// Work split: CTA k owns U hidden units j in [k*U, k*U+U) and the 4U gate rows that produce
+// them.  Its slice of W_hh (fp16, 4U x H) is loaded ONCE into shared memory in the canonical
+// no-swizzle K-major UMMA layout and stays there for all T steps (weight-stationary); c_t lives in
+// registers of the epilogue threads for the whole window.
+//
+// Per step:
+//   loader thread   waits on the grid barrier counter (acquire), then ONE cp.async.bulk brings the
+//                   72 KB h_{t-1} operand image (written by all CTAs, already in UMMA layout) into
+//                   shared memory
+//   MMA thread      H/16 tcgen05.mma (M=64, N=pad8(B), K=16): D[4U x B] in TMEM, commit -> mbarrier
+//   epilogue warps  tcgen05.ld D, add the prefetched XG slice, sigmoid/tanh, c/h update, dropout;
+//                   write activated gates + c_t (for backward), h_t as fp16 into (a) the next step's
+//                   operand image, (b) the row-major image the wgrad GEMM reads, (c) dropout(h_t) for
+//                   the next layer; then arrive on the grid barrier (release)
+//
+// Roofline: latency/L2 bound, not tensor bound -- per step each CTA streams its 144 KB weight slice
+// from shared memory through the tensor core (>= 1150 clk at 128 B/clk) and all CTAs re-read the
+// 72 KB h image from L2; algorithmic flops per layer call = 8*T*B*H^2.
+#include <cooperative_groups.h>
+
+#include "rec_common.cuh"
+
+namespace zrb {
+
+struct RecFwdArgs {
+    const __half* w_img;      // [nCTA][Kc][G][8][8]
+    __half* h_img;            // [T+1][Kc][GB][8][8]; image t is the B operand of step t
+    float* gates;             // [N,4H] in: x-part pre-activations (+biases); out: activated gates
+    const float* c0;          // [B,H]
+    float* cst;               // [N,H]
+    float* h_last;            // [B,H] or null
+    float* c_last;            // [B,H] or null
+    __half* hprev_h;          // [N+B,Hp] row-major, rows B.. written here
+    __half* y_h;              // [N,Hp] row-major dropout(h)
+    unsigned int* counter;    // grid barrier, zeroed before launch
+    int T, B, H, Hp, U, G, GB, Kc, nCTA;
+    MaskSrc m;
+};
+
+__global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int a_bytes = a.Kc * a.G * 128;
+    const int b_bytes = a.Kc * a.GB * 128;
+    const int Bp = a.GB * 8;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + a_bytes;
+    float* sD = (float*)(sB + b_bytes);                       // [64][Bp+1] staging of the accumulator
+    uint64_t* bars = (uint64_t*)((uint8_t*)sD + 64 * (Bp + 1) * 4);
+    uint64_t* bar_a = bars;        // weight slice landed
+    uint64_t* bar_b = bars + 1;    // h image of this step landed
+    uint64_t* bar_mma = bars + 2;  // accumulator ready
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const int j0 = cta * a.U;
+    const int nu = min(a.U, a.H - j0);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1); mbar_init(bar_b, 1); mbar_init(bar_mma, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc<32>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 5 && lane == 0) {
+        // ===================== loader =====================
+        const uint8_t* src = (const uint8_t*)a.w_img + (size_t)cta * a_bytes;
+        mbar_expect_tx(bar_a, a_bytes);
+        for (int off = 0; off < a_bytes; off += 32768) {
+            int n = min(32768, a_bytes - off);
+            bulk_load_1d(sA + off, src + off, n, bar_a);
+        }
+        for (int t = 0; t < a.T; ++t) {
+            if (t > 0) {
+                grid_counter_wait(a.counter, (unsigned int)t * a.nCTA);
+            }
+            fence_proxy_async_all();
+            mbar_expect_tx(bar_b, b_bytes);
+            bulk_load_1d(sB, (const uint8_t*)a.h_img + (size_t)t * b_bytes, b_bytes, bar_b);
+        }
+    } else if (warp == 4 && lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_f16(64, Bp, 0, 0);
+        const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+        const uint32_t lbo_a = a.G * 128, lbo_b = a.GB * 128;
+        bounded_mbar_wait(bar_a, 0);
+        for (int t = 0; t < a.T; ++t) {
+            bounded_mbar_wait(bar_b, t & 1);
+            tcgen05_fence_after();
+            const int ksteps = a.Kc / 2;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
+                uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
+                umma_f16(tmem_d, da, db, idesc, ks != 0 ? 1u : 0u);
+            }
+            umma_commit(bar_mma);
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue =====================
+        // accumulator row i = 4*u + q lives in TMEM lane (i % 16) + 32 * (i / 16): this warp holds
+        // units u = 4*warp .. 4*warp+3 in its lanes 0..15.  Cells (u, b) are dealt to the 32 lanes.
+        const int cells = 4 * Bp;
+        const int ncell = (cells + 31) / 32;      // <= 4 (Bp <= 32)
+        float creg[4];
+        const int B = a.B, H = a.H;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            creg[k] = 0.f;
+            int cell = lane + 32 * k;
+            if (k < ncell && cell < cells) {
+                int ul = cell / Bp, b = cell % Bp, u = 4 * warp + ul;
+                if (u < nu && b < B) creg[k] = a.c0[(size_t)b * H + j0 + u];
+            }
+        }
+        const uint64_t n_total = (uint64_t)a.T * B * H;
+        for (int t = 0; t < a.T; ++t) {
+            // prefetch the x-part pre-activations of this step while the MMAs run
+            float pre[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int cell = lane + 32 * k;
+                int ul = cell / Bp, b = cell % Bp, u = 4 * warp + ul;
+                bool ok = k < ncell && cell < cells && u < nu && b < B;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    pre[k][q] = ok ? __ldg(a.gates + ((size_t)t * B + b) * 4 * H + (size_t)q * H + j0 + u) : 0.f;
+            }
+            bounded_mbar_wait(bar_mma, t & 1);
+            tcgen05_fence_after();
+            // TMEM -> registers -> shared staging (rows 16*warp .. 16*warp+15 belong to this warp)
+            for (int c0 = 0; c0 < Bp; c0 += 8) {
+                uint32_t v[8];
+                tmem_ld_32x8(tmem_d + ((uint32_t)(32 * warp) << 16) + c0, v);
+                tmem_ld_wait();
+                if (lane < 16) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sD[(16 * warp + lane) * (Bp + 1) + c0 + i] = __uint_as_float(v[i]);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int cell = lane + 32 * k;
+                int ul = cell / Bp, b = cell % Bp, u = 4 * warp + ul;
+                bool ok = k < ncell && cell < cells && u < nu && b < B;
+                if (!ok) continue;
+                const float* d = sD + (16 * warp + 4 * ul) * (Bp + 1) + b;
+                float zi = pre[k][0] + d[0];
+                float zf = pre[k][1] + d[Bp + 1];
+                float zg = pre[k][2] + d[2 * (Bp + 1)];
+                float zo = pre[k][3] + d[3 * (Bp + 1)];
+                float gi = sigmoidf_(zi), gf = sigmoidf_(zf), gg = tanhf(zg), go = sigmoidf_(zo);
+                float c = gf * creg[k] + gi * gg;
+                float h = go * tanhf(c);
+                creg[k] = c;
+                const int j = j0 + u;
+                const size_t n = (size_t)t * B + b;
+                float* grow = a.gates + n * 4 * H + j;
+                grow[0] = gi; grow[H] = gf; grow[2 * (size_t)H] = gg; grow[3 * (size_t)H] = go;
+                a.cst[n * H + j] = c;
+                __half hh = __float2half_rn(h);
+                // next step's operand image: [kc][g][r][e], kc = j/8, e = j%8, g = b/8, r = b%8
+                __half* img = a.h_img + (size_t)(t + 1) * ((size_t)a.Kc * a.GB * 64);
+                img[((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7)] = hh;
+                a.hprev_h[((size_t)B + n) * a.Hp + j] = hh;
+                float y = h * mask_mul1(a.m, (uint64_t)n * H + j, n_total);
+                a.y_h[n * a.Hp + j] = __float2half_rn(y);
+                if (t == a.T - 1) {
+                    if (a.h_last) a.h_last[(size_t)b * H + j] = h;
+                    if (a.c_last) a.c_last[(size_t)b * H + j] = c;
+                }
+            }
+            // publish: all epilogue threads' global writes -> grid barrier arrival
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 0) {
+                __threadfence();
+                fence_proxy_async_all();
+                atomicAdd(a.counter, 1u);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 4) tmem_dealloc<32>(tmem_d);
+}
+
+// ---- weight / state image builders ---------------------------------------------------------------
+// w_img[cta][kc][g][r][e] = half(W_hh[q*H + cta*U + u, kc*8 + e]) with row i = g*8 + r = 4*u + q
+__global__ void pack_whh_fwd_kernel(const float* __restrict__ W, __half* __restrict__ img, int H, int U, int G, int Kc,
+                                    int nCTA) {
+    const size_t per_cta = (size_t)Kc * G * 64;
+    const size_t total = per_cta * nCTA;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int cta = (int)(idx / per_cta);
+        size_t r0 = idx % per_cta;
+        int e = (int)(r0 & 7), r = (int)((r0 >> 3) & 7);
+        int g = (int)((r0 >> 6) % G), kc = (int)((r0 >> 6) / G);
+        int i = g * 8 + r, u = i >> 2, q = i & 3;
+        int j = cta * U + u, k = kc * 8 + e;
+        float v = 0.f;
+        if (u < U && j < H && k < H) v = W[((size_t)q * H + j) * H + k];
+        img[idx] = __float2half_rn(v);
+    }
+}
+
+// image[kc][g][r][e] = half(h[b = g*8+r, k = kc*8+e])
+__global__ void pack_h_image_kernel(const float* __restrict__ h, __half* __restrict__ img, int B, int H, int GB,
+                                    int Kc) {
+    const int total = Kc * GB * 64;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int e = idx & 7, r = (idx >> 3) & 7, g = (idx >> 6) % GB, kc = (idx >> 6) / GB;
+        int b = g * 8 + r, k = kc * 8 + e;
+        img[idx] = __float2half_rn((b < B && k < H) ? h[(size_t)b * H + k] : 0.f);
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+int rec_fwd_plan(int H, int B, RecPlan* plan) {
+    int nsm = tc_num_sms();
+    int Kp = (H + 15) / 16 * 16;
+    plan->Kc = Kp / 8;
+    plan->GB = (B + 7) / 8;
+    plan->ok = 0;
+    if (plan->GB * 8 > 32) return ZRB_OK;  // TMEM allocation / staging sized for N <= 32
+    for (int U = 16; U >= 1; --U) {
+        int n = (H + U - 1) / U;
+        if (n > nsm) break;
+        int G = (4 * U + 7) / 8;
+        size_t smem = (size_t)plan->Kc * G * 128 + (size_t)plan->Kc * plan->GB * 128 +
+                      64 * (plan->GB * 8 + 1) * 4 + 64 + 256;
+        // the M=64 atom reads 8 row groups per K chunk: the last chunk reaches (8-G)*128 B past the
+        // slice, which must still be inside the allocation (it lands in the h image buffer)
+        if (smem <= 227 * 1024 && (8 - G) * 128 <= plan->Kc * plan->GB * 128) {
+            plan->U = U; plan->G = G; plan->nCTA = n; plan->smem = (int)smem; plan->ok = 1;
+            return ZRB_OK;
+        }
+    }
+    return ZRB_OK;
+}
+
+int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s) {
+    pack_whh_fwd_kernel<<<148 * 4, 256, 0, s>>>(W, img, H, p.U, p.G, p.Kc, p.nCTA);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+int pack_h_image(const float* h, __half* img, int B, int H, const RecPlan& p, cudaStream_t s) {
+    pack_h_image_kernel<<<cdiv(p.Kc * p.GB * 64, 256), 256, 0, s>>>(h, img, B, H, p.GB, p.Kc);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+int lstm_rec_fwd(const RecPlan& p, const __half* w_img, __half* h_img, float* gates, const float* c0, float* cst,
+                 float* h_last, float* c_last, __half* hprev_h, __half* y_h, unsigned int* counter, int T, int B, int H,
+                 int Hp, MaskSrc m, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    ZRB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+    RecFwdArgs a;
+    a.w_img = w_img; a.h_img = h_img; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;
+    a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter;
+    a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
+    void* args[] = {&a};
+    ZRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_kernel, dim3(p.nCTA), dim3(kRecThreads), args,
+                                         (size_t)p.smem, s));
+    count_launch();
+    return ZRB_OK;
+}
+
+}  // namespace zrb

@@ -39,8 +39,8 @@ int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s) {
 }
 
 // out[j] = inv_scale * sum_n A[n, j]  for an fp16 matrix with pitch ld
-__global__ void colsum_h_kernel(const __half* __restrict__ A, int64_t ld, float* __restrict__ out, int N, int M,
-                                float inv_scale) {
+__global__ void colsum_h_kernel(const __half* __restrict__ A, int64_t ld, float* __restrict__ out,
+                                float* __restrict__ out2, int N, int M, float inv_scale) {
     __shared__ float part[8][33];
     int col = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
@@ -53,11 +53,12 @@ __global__ void colsum_h_kernel(const __half* __restrict__ A, int64_t ld, float*
 #pragma unroll
         for (int r = 0; r < 8; ++r) t += part[r][threadIdx.x];
         out[col] = t * inv_scale;
+        if (out2) out2[col] = t * inv_scale;
     }
 }
-int colsum_h(const __half* A, int64_t ld, float* out, int N, int M, float inv_scale, cudaStream_t s) {
+int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, cudaStream_t s) {
     dim3 blk(32, 8);
-    colsum_h_kernel<<<cdiv(M, 32), blk, 0, s>>>(A, ld, out, N, M, inv_scale);
+    colsum_h_kernel<<<cdiv(M, 32), blk, 0, s>>>(A, ld, out, out2, N, M, inv_scale);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
