@@ -299,8 +299,9 @@ def test_large_config_against_fp64_oracle(engine):
     m.zero_grad()
     scores, _ = m(x, m.state_init(B))
     (2.0 * _caller_nll_loss(scores, y)).backward()
+    lin = 2e-5 if engine == "simt" else 2e-3   # fp16 images round differently near the subnormal range
     for k, p in m.named_parameters():
-        assert torch.allclose(p.grad, 2.0 * g1[k], rtol=1e-3, atol=1e-7 + 1e-4 * g1[k].abs().max().item()), k
+        _scale_close(p.grad.cpu().numpy(), 2.0 * g1[k].cpu().numpy(), lin, f"linearity {k}")
     grads = O.model_bwd(params, cache, O.nll_loss_bwd(sc, y.numpy()), L)
     for k in grads:
         _scale_close(g1[k].cpu().numpy(), grads[k], tol["grad"], f"L grad {k}")

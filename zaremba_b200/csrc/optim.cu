@@ -1,41 +1,56 @@
 // clip_grad_norm_ + SGD over a list of tensors -- main.py:114-117.
-// Pure HBM streaming: pass 1 reads every gradient once (sum of squares), pass 2 reads
-// g and p and writes g and p.  Algorithmic bytes per parameter element: 4 (norm) + 16.
+// Pure HBM streaming.  Pass 1 reads every gradient once (sum of squares); pass 2 reads g and p and
+// writes g and p (and, for the tensor-core engine, the fp16 operand images of the new weights, so the
+// weights are not re-read by a separate pack pass).  Algorithmic bytes per parameter element:
+// 4 (norm) + 16 (update) [+ 2..6 for fp16 images of the matrices].
+// Tensors that are adjacent in memory (the Trainer's flat buffers) are coalesced into one run and
+// streamed with 128-bit accesses.
 #include "kernels.h"
 
 namespace zrb {
 
-constexpr int kNormBlocks = 592;  // 4 x 148 SMs
+constexpr int kNormBlocks = 148 * 8;
 constexpr int kThreads = 256;
 
-// flat virtual index space over all tensors; each block walks a contiguous slice of it
-__global__ void sumsq_kernel(TensorList tl, int64_t total, float* __restrict__ partials) {
-    __shared__ float sh[kThreads / 32];
-    int64_t per = (total + gridDim.x - 1) / gridDim.x;
-    per = (per + 3) & ~(int64_t)3;
-    int64_t lo = per * blockIdx.x, hi = lo + per < total ? lo + per : total;
-    float acc = 0.f;
-    int64_t base = 0;
-    for (int t = 0; t < tl.count; ++t) {
-        int64_t n = tl.n[t];
-        int64_t a = lo > base ? lo : base, b = hi < base + n ? hi : base + n;
-        if (a < b) {
-            const float* g = tl.g[t] - base;
-            for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
-                float v = g[i];
-                acc += v * v;
-            }
-        }
-        base += n;
-    }
+__device__ __forceinline__ float block_sum(float acc, float* sh) {
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
+    float v = 0.f;
     if (threadIdx.x < 32) {
-        float v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
+        v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.f;
         v = warp_sum(v);
-        if (threadIdx.x == 0) partials[blockIdx.x] = v;
     }
+    return v;
+}
+
+// one run of `n` floats; partials[blockIdx.x] += sum of squares of this block's grid-stride share
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials, int accumulate) {
+    __shared__ float sh[kThreads / 32];
+    float acc = 0.f;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)g) & 15) == 0) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        const int64_t n4 = n >> 2;
+        int64_t i = tid;
+        for (; i + 3 * stride < n4; i += 4 * stride) {   // 4 independent 16-byte loads in flight
+            float4 a = __ldcs(g4 + i), b = __ldcs(g4 + i + stride), c = __ldcs(g4 + i + 2 * stride),
+                   d = __ldcs(g4 + i + 3 * stride);
+            acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            acc += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+            acc += c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
+            acc += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+        }
+        for (; i < n4; i += stride) {
+            float4 a = __ldcs(g4 + i);
+            acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        }
+        for (int64_t j = (n4 << 2) + tid; j < n; j += stride) acc += g[j] * g[j];
+    } else {
+        for (int64_t j = tid; j < n; j += stride) acc += g[j] * g[j];
+    }
+    float v = block_sum(acc, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = accumulate ? partials[blockIdx.x] + v : v;
 }
 
 // scalars[0] = norm, scalars[1] = clip coefficient  (double accumulation of the partials)
@@ -59,38 +74,80 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partials, int n, 
     }
 }
 
-__global__ void clip_sgd_update_kernel(TensorList tl, int64_t total, float lr, const float* __restrict__ scalars) {
-    float coef = scalars[1];
-    int64_t per = (total + gridDim.x - 1) / gridDim.x;
-    int64_t lo = per * blockIdx.x, hi = lo + per < total ? lo + per : total;
-    int64_t base = 0;
-    for (int t = 0; t < tl.count; ++t) {
-        int64_t n = tl.n[t];
-        int64_t a = lo > base ? lo : base, b = hi < base + n ? hi : base + n;
-        if (a < b) {
-            float* g = tl.g[t] - base;
-            float* p = tl.p[t] - base;
-            for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
-                float gv = g[i] * coef;     // clip_grad_norm_ scales .grad in place
-                g[i] = gv;
-                p[i] -= lr * gv;            // main.py:117
-            }
+// g *= coef (clip_grad_norm_ scales .grad in place); p -= lr * g (main.py:117)
+__global__ void clip_sgd_update_kernel(float* __restrict__ p, float* __restrict__ g, int64_t n, float lr,
+                                       const float* __restrict__ scalars) {
+    const float coef = scalars[1];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (((((uintptr_t)g) | ((uintptr_t)p)) & 15) == 0) {
+        float4* g4 = reinterpret_cast<float4*>(g);
+        float4* p4 = reinterpret_cast<float4*>(p);
+        const int64_t n4 = n >> 2;
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 gv = __ldcs(g4 + i), pv = __ldcs(p4 + i);
+            gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;
+            pv.x -= lr * gv.x; pv.y -= lr * gv.y; pv.z -= lr * gv.z; pv.w -= lr * gv.w;
+            __stcs(g4 + i, gv);
+            __stcs(p4 + i, pv);
         }
-        base += n;
+        for (int64_t j = (n4 << 2) + tid; j < n; j += stride) {
+            float gv = g[j] * coef;
+            g[j] = gv;
+            p[j] -= lr * gv;
+        }
+    } else {
+        for (int64_t j = tid; j < n; j += stride) {
+            float gv = g[j] * coef;
+            g[j] = gv;
+            p[j] -= lr * gv;
+        }
     }
+}
+
+// merge tensors that are adjacent in memory (both p and g) into runs
+static int coalesce(const TensorList& tl, float** p, float** g, int64_t* n) {
+    int runs = 0;
+    for (int t = 0; t < tl.count; ++t) {
+        if (tl.n[t] == 0) continue;
+        if (runs && p[runs - 1] + n[runs - 1] == tl.p[t] && g[runs - 1] + n[runs - 1] == tl.g[t]) {
+            n[runs - 1] += tl.n[t];
+        } else {
+            p[runs] = tl.p[t]; g[runs] = tl.g[t]; n[runs] = tl.n[t];
+            ++runs;
+        }
+    }
+    return runs;
+}
+
+static int blocks_for(int64_t n) {
+    int64_t b = (n / 4 + kThreads - 1) / kThreads;
+    if (b < 1) b = 1;
+    return (int)(b > kNormBlocks ? kNormBlocks : b);
+}
+
+int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,
+              cudaStream_t s) {
+    float* p[16]; float* g[16]; int64_t n[16];
+    int runs = coalesce(tl, p, g, n);
+    ZRB_CUDA(cudaMemsetAsync(partials, 0, kNormBlocks * sizeof(float), s));
+    for (int r = 0; r < runs; ++r) {
+        sumsq_kernel<<<blocks_for(n[r]), kThreads, 0, s>>>(g[r], n[r], partials, 1);
+        ZRB_KERNEL_CHECK();
+    }
+    norm_finalize_kernel<<<1, 256, 0, s>>>(partials, kNormBlocks, max_norm, scalars, norm_out);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
 }
 
 int clip_sgd(const TensorList& tl, float lr, float max_norm, float* partials, float* scalars, float* norm_out,
              cudaStream_t s) {
-    int64_t total = 0;
-    for (int t = 0; t < tl.count; ++t) total += tl.n[t];
-    if (!total) return ZRB_OK;
-    sumsq_kernel<<<kNormBlocks, kThreads, 0, s>>>(tl, total, partials);
-    ZRB_KERNEL_CHECK();
-    norm_finalize_kernel<<<1, 256, 0, s>>>(partials, kNormBlocks, max_norm, scalars, norm_out);
-    ZRB_KERNEL_CHECK();
-    clip_sgd_update_kernel<<<kNormBlocks * 2, kThreads, 0, s>>>(tl, total, lr, scalars);
-    ZRB_KERNEL_CHECK();
+    ZRB_TRY(grad_norm(tl, max_norm, partials, scalars, norm_out, s));
+    float* p[16]; float* g[16]; int64_t n[16];
+    int runs = coalesce(tl, p, g, n);
+    for (int r = 0; r < runs; ++r) {
+        clip_sgd_update_kernel<<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
+        ZRB_KERNEL_CHECK();
+    }
     return ZRB_OK;
 }
 
