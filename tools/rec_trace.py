@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Phase timeline of the persistent recurrence kernels (zrb_prof_rec_trace): mean clocks per phase."""
+import os, sys, json, ctypes as C
+os.environ["ZRB_REC_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import zaremba_b200
+from zaremba_b200 import _lib
+from bench import CONFIGS
+
+c = CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "large"]
+V, H, L, T, B = c["V"], c["H"], c["L"], c["T"], c["B"]
+torch.manual_seed(1)
+m = zaremba_b200.Model(V, H, L, c["p"], c["winit"]).cuda(); m.train()
+tr = zaremba_b200.Trainer(m, B, T)
+g = torch.Generator().manual_seed(2)
+for i in range(6):
+    d = torch.randint(0, V, (B, T + 1), generator=g)
+    tr.train_step(d[:, :T].t().contiguous().cuda(), d[:, 1:].t().contiguous().cuda(), c["lr"], c["clip"])
+buf = (C.c_int64 * (2 * T * 8))()
+n = _lib.load().zrb_prof_rec_trace(tr.ctx, buf, 2 * T * 8)
+assert n == 2 * T * 8, n
+a = np.array(buf[:], dtype=np.int64).reshape(2, T, 8)
+names = ["barrier_seen", "operand_landed", "mma_issued", "acc_ready", "tmem_drained", "cells_begin/end", "pre_arrive", "arrived"]
+out = {}
+for d, nm in enumerate(["fwd", "bwd"]):
+    x = a[d][2:T - 1]                       # steady-state steps
+    step = np.diff(a[d][1:, 0]).mean()
+    rel = (x - x[:, :1]).mean(0)
+    out[nm] = {"clk_per_step": float(step), "phase_offsets_clk": dict(zip(names, [float(v) for v in rel]))}
+print(json.dumps(out, indent=1))

@@ -67,6 +67,7 @@ _SIGNATURES = {
                                       C.c_uint64, C.c_float, C.c_float, _vp, _vp, _vp]),
     "zrb_prof_enable": (C.c_int, [_vp, C.c_int32]),
     "zrb_prof_read": (C.c_int, [_vp, _vp, _vp]),
+    "zrb_prof_rec_trace": (C.c_int, [_vp, _vp, C.c_int32]),
     "zrb_gemm_f32": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                C.c_float, _vp]),
     "zrb_gemm_f16": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int64, C.c_int32, _vp, C.c_int64, C.c_int32,

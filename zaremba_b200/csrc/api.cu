@@ -304,6 +304,12 @@ int zrb_prof_read(zrb_ctx* c, float* h_ms, int64_t* h_counts) {
     return ZRB_OK;
 }
 
+int zrb_prof_rec_trace(zrb_ctx* c, int64_t* h_out, int32_t max_entries) {
+    ZRB_REQUIRE(c && h_out, "null argument");
+    if (c->cfg.engine != ZRB_ENGINE_TC) { set_error("recurrence trace needs the tcgen05 engine"); return ZRB_E_STATE; }
+    return tc_rec_trace(c, (long long*)h_out, max_entries);
+}
+
 int zrb_gemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t transA,
                  int32_t transB, float alpha, float beta, void* stream) {
     ZRB_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0, "bad gemm args");

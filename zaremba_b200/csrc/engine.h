@@ -73,6 +73,7 @@ int tc_backward(zrb_ctx* c, const zrb_params* p, const float* dscores, const zrb
 int tc_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, const int64_t* x, const int64_t* y,
                         int T, int B, const zrb_states* in, const zrb_states* out, uint64_t seed, uint64_t step,
                         float* loss, cudaStream_t s);
+int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries);
 int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
               cudaStream_t s);
 

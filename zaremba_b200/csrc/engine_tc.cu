@@ -25,6 +25,7 @@ struct zrb_tc_state {
     __half* dG_h = nullptr;
     __half* dS_h = nullptr;
     int64_t packed_version = 0;
+    zrb_params packed_params{};
     std::vector<void*> allocs;
     // persistent recurrence
     zrb::RecPlan fplan{};
@@ -34,6 +35,7 @@ struct zrb_tc_state {
     zrb::RecPlan bplan{};
     __half* w_img_b[ZRB_MAX_LAYERS] = {};
     __half* g_img = nullptr;
+    long long* trace = nullptr;   // [2][T][8] clock stamps (zrb_prof_rec_trace)
 };
 
 namespace zrb {
@@ -88,6 +90,7 @@ int tc_ctx_init(zrb_ctx* c) {
         ZRB_TRY(tc_alloc(c, &t->h_img, (size_t)(c->cfg.max_seq + 1) * fp.Kc * fp.GB * 64));
         ZRB_TRY(tc_alloc(c, &t->counter, 64));
     }
+    if (getenv("ZRB_REC_TRACE")) ZRB_TRY(tc_alloc(c, &t->trace, (size_t)2 * c->cfg.max_seq * 8));
     ZRB_TRY(rec_bwd_plan(H, c->cfg.max_batch, &t->bplan));
     if (!t->fplan.ok || (force && !strcmp(force, "fwdonly"))) t->bplan.ok = 0;
     if (t->bplan.ok) {
@@ -108,7 +111,7 @@ void tc_ctx_free(zrb_ctx* c) {
 // rebuild the fp16 weight images when parameter values changed (main.py:116-117 / zrb_clip_sgd)
 static int tc_pack_weights(zrb_ctx* c, const zrb_params* p, cudaStream_t s) {
     zrb_tc_state* t = c->tc;
-    if (t->packed_version == c->weights_version) return ZRB_OK;
+    if (t->packed_version == c->weights_version && !memcmp(&t->packed_params, p, sizeof(*p))) return ZRB_OK;
     ProfScope ps(c, ZRB_PROF_PACK, s);
     const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
     for (int l = 0; l < L; ++l) {
@@ -120,6 +123,7 @@ static int tc_pack_weights(zrb_ctx* c, const zrb_params* p, cudaStream_t s) {
     }
     ZRB_TRY(convert_pad_f16(p->fc_w, H, t->fc_w_h, t->Hp, V, H, 1.f, s));
     t->packed_version = c->weights_version;
+    t->packed_params = *p;
     return ZRB_OK;
 }
 
@@ -151,7 +155,7 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
         if (t->fplan.ok) {
             ZRB_TRY(pack_h_image(c->h0s[l], t->h_img, B, H, t->fplan, s));
             ZRB_TRY(lstm_rec_fwd(t->fplan, t->w_img_f[l], t->h_img, G, c->c0s[l], c->cst[l], out->h[l], out->c[l],
-                                 t->hprev_h[l], t->x_h[l + 1], t->counter, T, B, H, Hp, m, s));
+                                 t->hprev_h[l], t->x_h[l + 1], t->counter, T, B, H, Hp, m, s, t->trace));
             continue;
         }
         for (int tt = 0; tt < T; ++tt) {
@@ -196,7 +200,7 @@ static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_par
         if (t->bplan.ok) {
             ProfScope ps(c, ZRB_PROF_REC_BWD, s);
             ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], t->dG_h,
-                                 t->counter, T, B, H, G4p, m, s));
+                                 t->counter, T, B, H, G4p, m, s, t->trace ? t->trace + (size_t)c->cfg.max_seq * 8 : nullptr));
         } else {
             ProfScope ps(c, ZRB_PROF_REC_BWD, s);
             for (int tt = T - 1; tt >= 0; --tt) {
@@ -249,13 +253,55 @@ int tc_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
     return tc_backward_from_image(c, p, g, s);
 }
 
+int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries) {
+    if (!c->tc || !c->tc->trace) { set_error("set ZRB_REC_TRACE=1 before creating the context"); return ZRB_E_STATE; }
+    int n = 2 * c->cfg.max_seq * 8;
+    if (n > max_entries) n = max_entries;
+    ZRB_CUDA(cudaDeviceSynchronize());
+    ZRB_CUDA(cudaMemcpy(h_out, c->tc->trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    return n;
+}
+
+// clip + SGD (main.py:114-117).  With 16-byte-aligned matrices (H % 4 == 0) the update pass also
+// writes the fp16 operand images of the new weights, so the next forward needs no pack pass.
 int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
               cudaStream_t s) {
-    {
-        ProfScope ps(c, ZRB_PROF_CLIP_SGD, s);
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
+    bool fuse = (H % 4 == 0);
+    for (int i = 0; i < tl.count && fuse; ++i)
+        fuse = ((((uintptr_t)tl.p[i]) | ((uintptr_t)tl.g[i])) & 15) == 0;
+    ProfScope ps(c, ZRB_PROF_CLIP_SGD, s);
+    if (!fuse) {
         ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, s));
+        c->weights_version++;
+        return ZRB_OK;
     }
+    ZRB_TRY(grad_norm(tl, max_norm, c->partials, c->scalars, norm_out, s));
+    // tensor order of param_list(): embed, (w_ih, w_hh, b_ih, b_hh) x L, fc_w, fc_b
+    TensorList rest;
+    rest.count = 0;
+    auto push = [&](int i) { rest.p[rest.count] = tl.p[i]; rest.g[rest.count] = tl.g[i]; rest.n[rest.count] = tl.n[i]; rest.count++; };
+    push(0);
+    const bool persistent = t->fplan.ok && t->bplan.ok;
+    for (int l = 0; l < L; ++l) {
+        const int b = 1 + 4 * l;
+        ZRB_TRY(update_pack(tl.p[b], tl.g[b], 4 * H, H, lr, c->scalars, t->w_ih_h[l], t->Hp, nullptr, nullptr, nullptr,
+                            nullptr, s));
+        ZRB_TRY(update_pack(tl.p[b + 1], tl.g[b + 1], 4 * H, H, lr, c->scalars, persistent ? nullptr : t->w_hh_h[l],
+                            t->Hp, t->fplan.ok ? t->w_img_f[l] : nullptr, &t->fplan,
+                            t->bplan.ok ? t->w_img_b[l] : nullptr, &t->bplan, s));
+        push(b + 2);
+        push(b + 3);
+    }
+    const int f = 1 + 4 * L;
+    ZRB_TRY(update_pack(tl.p[f], tl.g[f], V, H, lr, c->scalars, t->fc_w_h, t->Hp, nullptr, nullptr, nullptr, nullptr, s));
+    push(f + 1);
+    ZRB_TRY(sgd_apply(rest, lr, c->scalars, s));
+    for (int l = 0; l < L; ++l) ZRB_TRY(add_vec(p->b_ih[l], p->b_hh[l], t->bsum[l], 4 * H, s));
     c->weights_version++;
+    t->packed_version = c->weights_version;      // images are current
+    t->packed_params = *p;
     return ZRB_OK;
 }
 

@@ -42,6 +42,7 @@ struct TensorList {
 // partials: >= 1024 floats scratch; scalars: >= 4 floats (norm, coef)
 int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,
               cudaStream_t s);
+int sgd_apply(const TensorList& tl, float lr, const float* scalars, cudaStream_t s);
 int clip_sgd(const TensorList& tl, float lr, float max_norm, float* partials, float* scalars, float* norm_out,
              cudaStream_t s);
 

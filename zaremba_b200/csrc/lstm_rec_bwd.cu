@@ -30,6 +30,7 @@ struct RecBwdArgs {
     unsigned int* counter;
     int T, B, H, G4p, U, G, GB, Kc, nCTA;
     MaskSrc m;
+    long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         for (int s = 1; s < T; ++s) {
             const int t = T - 1 - s;                      // step being computed; needs dG_{t+1}
             grid_counter_wait(a.counter, (unsigned int)s * a.nCTA);
+            if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 0] = clock64();
             fence_proxy_async_all();
             mbar_expect_tx(bar_b, b_bytes);
             const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + rank) * b_bytes;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         for (int s = 1; s < T; ++s) {
             bounded_mbar_wait(bar_b, (s - 1) & 1);
             tcgen05_fence_after();
+            if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 1] = clock64();
             const int ksteps = a.Kc / 2;
             for (int ks = 0; ks < ksteps; ++ks) {
                 uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 umma_f16(tmem_d, da, db, idesc, ks != 0 ? 1u : 0u);
             }
             umma_commit(bar_mma);
+            if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 2] = clock64();
         }
     } else if (warp < 4) {
         // ===================== epilogue: 128 threads, cells (u, b) of this CTA's U units =====================
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             if (s > 0) {
                 bounded_mbar_wait(bar_mma, (s - 1) & 1);
                 tcgen05_fence_after();
+                if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 3] = clock64();
                 // TMEM -> own shared staging: accumulator row i (cluster-local unit) in lane (i%16)+32*(i/16)
                 for (int c0 = 0; c0 < Bp; c0 += 8) {
                     uint32_t v[8];
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 }
                 tcgen05_fence_before();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 4] = clock64();
                 if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
                 {   // wait until all four CTAs of the cluster staged their partials
                     uint32_t n = 0; long long t0 = 0;
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     }
                 }
             }
+            if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 5] = clock64();
 #pragma unroll
             for (int k = 0; k < kMaxCell; ++k) {
                 int cell = tid + 128 * k;
@@ -232,11 +239,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     img[(size_t)q * ((size_t)a.Kc * a.GB * 64)] = hv;
                 }
             }
+            if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 6] = clock64();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 0) {
                 __threadfence();
                 fence_proxy_async_all();
                 atomicAdd(a.counter, 1u);
+                if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 7] = clock64();
             }
         }
     }
@@ -305,7 +314,7 @@ int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
 
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
                  const float* cst, const float* c0, __half* dG_h, unsigned int* counter, int T, int B, int H, int G4p,
-                 MaskSrc m, cudaStream_t s) {
+                 MaskSrc m, cudaStream_t s, long long* trace) {
     static bool attr = false;
     if (!attr) {
         ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -315,7 +324,7 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     RecBwdArgs a;
     a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
     a.counter = counter;
-    a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
+    a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.nCTA);
     cfg.blockDim = dim3(kRecThreads);

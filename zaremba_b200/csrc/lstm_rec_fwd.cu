@@ -39,6 +39,7 @@ struct RecFwdArgs {
     unsigned int* counter;    // grid barrier, zeroed before launch
     int T, B, H, Hp, U, G, GB, Kc, nCTA;
     MaskSrc m;
+    long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
 };
 
 __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs a) {
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             if (t > 0) {
                 grid_counter_wait(a.counter, (unsigned int)t * a.nCTA);
             }
+            if (a.trace && cta == 0) a.trace[t * 8 + 0] = clock64();
             fence_proxy_async_all();
             mbar_expect_tx(bar_b, b_bytes);
             bulk_load_1d(sB, (const uint8_t*)a.h_img + (size_t)t * b_bytes, b_bytes, bar_b);
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         for (int t = 0; t < a.T; ++t) {
             bounded_mbar_wait(bar_b, t & 1);
             tcgen05_fence_after();
+            if (a.trace && cta == 0) a.trace[t * 8 + 1] = clock64();
             const int ksteps = a.Kc / 2;
             for (int ks = 0; ks < ksteps; ++ks) {
                 uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 umma_f16(tmem_d, da, db, idesc, ks != 0 ? 1u : 0u);
             }
             umma_commit(bar_mma);
+            if (a.trace && cta == 0) a.trace[t * 8 + 2] = clock64();
         }
     } else if (warp < 4) {
         // ===================== epilogue =====================
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             }
             bounded_mbar_wait(bar_mma, t & 1);
             tcgen05_fence_after();
+            if (a.trace && cta == 0 && threadIdx.x == 0) a.trace[t * 8 + 3] = clock64();
             // TMEM -> registers -> shared staging (rows 16*warp .. 16*warp+15 belong to this warp)
             for (int c0 = 0; c0 < Bp; c0 += 8) {
                 uint32_t v[8];
@@ -148,6 +153,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             }
             tcgen05_fence_before();
             __syncwarp();
+            if (a.trace && cta == 0 && threadIdx.x == 0) a.trace[t * 8 + 4] = clock64();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int cell = lane + 32 * k;
@@ -181,11 +187,14 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 }
             }
             // publish: all epilogue threads' global writes -> grid barrier arrival
+            if (a.trace && cta == 0 && threadIdx.x == 0) a.trace[t * 8 + 5] = clock64();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 0) {
+                if (a.trace && cta == 0) a.trace[t * 8 + 6] = clock64();
                 __threadfence();
                 fence_proxy_async_all();
                 atomicAdd(a.counter, 1u);
+                if (a.trace && cta == 0) a.trace[t * 8 + 7] = clock64();
             }
         }
     }
@@ -264,7 +273,7 @@ int pack_h_image(const float* h, __half* img, int B, int H, const RecPlan& p, cu
 
 int lstm_rec_fwd(const RecPlan& p, const __half* w_img, __half* h_img, float* gates, const float* c0, float* cst,
                  float* h_last, float* c_last, __half* hprev_h, __half* y_h, unsigned int* counter, int T, int B, int H,
-                 int Hp, MaskSrc m, cudaStream_t s) {
+                 int Hp, MaskSrc m, cudaStream_t s, long long* trace) {
     static bool attr = false;
     if (!attr) {
         ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -274,7 +283,7 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, __half* h_img, float* ga
     RecFwdArgs a;
     a.w_img = w_img; a.h_img = h_img; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;
     a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter;
-    a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
+    a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     void* args[] = {&a};
     ZRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_kernel, dim3(p.nCTA), dim3(kRecThreads), args,
                                          (size_t)p.smem, s));

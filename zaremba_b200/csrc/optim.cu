@@ -139,6 +139,17 @@ int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scal
     return ZRB_OK;
 }
 
+// update only (norm / coefficient already in `scalars`)
+int sgd_apply(const TensorList& tl, float lr, const float* scalars, cudaStream_t s) {
+    float* p[16]; float* g[16]; int64_t n[16];
+    int runs = coalesce(tl, p, g, n);
+    for (int r = 0; r < runs; ++r) {
+        clip_sgd_update_kernel<<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
+        ZRB_KERNEL_CHECK();
+    }
+    return ZRB_OK;
+}
+
 int clip_sgd(const TensorList& tl, float lr, float max_norm, float* partials, float* scalars, float* norm_out,
              cudaStream_t s) {
     ZRB_TRY(grad_norm(tl, max_norm, partials, scalars, norm_out, s));
