@@ -6,5 +6,6 @@ ahmetumutdurmus/zaremba behind the reference's `model.Model` interface.
 """
 from .model import Model, Embed, LSTM, Linear  # noqa: F401
 from .trainer import Trainer, minibatch  # noqa: F401
+from . import ensemble, parallel  # noqa: F401
 
 __all__ = ["Model", "Embed", "LSTM", "Linear", "Trainer", "minibatch"]

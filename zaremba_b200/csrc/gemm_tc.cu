@@ -25,7 +25,8 @@ using namespace tc;
 constexpr int GBM = 128, GBN = 128, GBK = 64;
 constexpr int kStages = 6, kAccStages = 2;
 constexpr int kABytes = GBM * GBK * 2, kBBytes = GBN * GBK * 2;
-constexpr int kGemmSmem = kStages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kEpiBytes = 4 * 32 * 33 * 4;   // per-epilogue-warp 32x32 transpose tile (padded)
+constexpr int kGemmSmem = kStages * (kABytes + kBBytes) + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kGemmThreads = 256;
 
 struct GemmArgs {
@@ -36,6 +37,7 @@ struct GemmArgs {
     int64_t ldc;
     int accumulate;
     int tiles_m, tiles_n;
+    int splits;      // split-K factor (1 or 2); with 2 the epilogue adds atomically into a zeroed C
 };
 
 template <bool A_MN, bool B_MN>
@@ -45,16 +47,20 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + kStages * kABytes;
-    uint64_t* bars = (uint64_t*)(smem + kStages * (kABytes + kBBytes));
+    float* sEpi = (float*)(smem + kStages * (kABytes + kBBytes));
+    uint64_t* bars = (uint64_t*)(smem + kStages * (kABytes + kBBytes) + kEpiBytes);
     uint64_t* full = bars;                       // [kStages]
     uint64_t* empty = bars + kStages;            // [kStages]
     uint64_t* acc_full = bars + 2 * kStages;     // [kAccStages]
     uint64_t* acc_empty = acc_full + kAccStages; // [kAccStages]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + kAccStages);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n;
     const int num_kb = (p.K + GBK - 1) / GBK;
+    const int num_work = num_tiles * p.splits;            // work item w: tile = w % num_tiles, K range = w / num_tiles
+    const int kb_per = (num_kb + p.splits - 1) / p.splits;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_a);
@@ -72,9 +78,10 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
         int s = 0; uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int tile = w % num_tiles, kb0 = (w / num_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
             const int m0 = (tile % p.tiles_m) * GBM, n0 = (tile / p.tiles_m) * GBN;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], kABytes + kBBytes);
                 uint8_t* a = sA + s * kABytes;
@@ -98,11 +105,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_f16(GBM, GBN, A_MN ? 1 : 0, B_MN ? 1 : 0);
         int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int kb0 = (w / num_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
             mbar_wait(&acc_empty[as], aph ^ 1);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + as * GBN;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[s], ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * kABytes), b_addr = smem_u32(sB + s * kBBytes);
@@ -115,7 +123,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                                        : make_smem_desc(a_addr + k * 32, 16, 1024, kSwizzle128B);
                     uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, kBBytes / 2, 1024, kSwizzle128B)
                                        : make_smem_desc(b_addr + k * 32, 16, 1024, kSwizzle128B);
-                    umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty[s]);
                 if (++s == kStages) { s = 0; ph ^= 1; }
@@ -125,52 +133,42 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
+        // tcgen05.ld hands thread i of the warp accumulator row 32q+i; a padded 32x32 shared-memory
+        // transpose turns that into row-contiguous 128-byte global stores (one row per instruction).
         const int q = warp - 4;  // TMEM lanes [32q, 32q+32)
+        float* sw = sEpi + q * 32 * 33;
         int as = 0; uint32_t aph = 0;
-        const bool vec_ok = (p.ldc % 4 == 0) && ((((uintptr_t)p.C) & 15) == 0);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+            const int tile = w % num_tiles, split = w / num_tiles;
             const int m0 = (tile % p.tiles_m) * GBM, n0 = (tile / p.tiles_m) * GBN;
+            const bool has_k = split * kb_per < num_kb;
             mbar_wait(&acc_full[as], aph);
             tcgen05_fence_after();
-            const int row = m0 + q * 32 + lane;
-            float* crow = p.C + (int64_t)row * p.ldc;
+            const bool add_bias = p.bias != nullptr && split == 0;
 #pragma unroll 1
             for (int c = 0; c < GBN / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * GBN + c * 32, v);
                 tmem_ld_wait();
                 const int nb = n0 + c * 32;
-                if (row < p.M && nb < p.N) {
-                    if (vec_ok && nb + 32 <= p.N) {
+                if (nb < p.N && m0 + q * 32 < p.M) {            // warp-uniform
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o;
-                            o.x = p.alpha * __uint_as_float(v[j]);
-                            o.y = p.alpha * __uint_as_float(v[j + 1]);
-                            o.z = p.alpha * __uint_as_float(v[j + 2]);
-                            o.w = p.alpha * __uint_as_float(v[j + 3]);
-                            if (p.bias) {
-                                float4 bb = *reinterpret_cast<const float4*>(p.bias + nb + j);
-                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                            }
-                            float4* dst = reinterpret_cast<float4*>(crow + nb + j);
-                            if (p.accumulate) {
-                                float4 old = *dst;
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                            }
-                            *dst = o;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (nb + j < p.N) {
-                                float o = p.alpha * __uint_as_float(v[j]);
-                                if (p.bias) o += p.bias[nb + j];
-                                if (p.accumulate) o += crow[nb + j];
-                                crow[nb + j] = o;
-                            }
+                    for (int j = 0; j < 32; ++j) sw[lane * 33 + j] = has_k ? p.alpha * __uint_as_float(v[j]) : 0.f;
+                    __syncwarp();
+                    const int col = nb + lane;
+                    const float bv = (add_bias && col < p.N) ? p.bias[col] : 0.f;
+                    const int rows = min(32, p.M - (m0 + q * 32));
+                    if (col < p.N) {
+                        float* cptr = p.C + (int64_t)(m0 + q * 32) * p.ldc + col;
+                        if (p.splits > 1) {
+                            for (int r = 0; r < rows; ++r) atomicAdd(cptr + (int64_t)r * p.ldc, sw[r * 33 + lane] + bv);
+                        } else if (p.accumulate) {
+                            for (int r = 0; r < rows; ++r) cptr[(int64_t)r * p.ldc] += sw[r * 33 + lane] + bv;
+                        } else {
+                            for (int r = 0; r < rows; ++r) cptr[(int64_t)r * p.ldc] = sw[r * 33 + lane] + bv;
                         }
                     }
+                    __syncwarp();
                 }
             }
             tcgen05_fence_before();
@@ -253,7 +251,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
         ZRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         g_attr_set[idx] = true;
     }
-    int grid = a.tiles_m * a.tiles_n;
+    int grid = a.tiles_m * a.tiles_n * a.splits;
     if (grid > tc_num_sms()) grid = tc_num_sms();
     kern<<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, a);
     ZRB_KERNEL_CHECK();
@@ -272,6 +270,13 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.bias = bias; a.C = C; a.ldc = ldc; a.accumulate = accumulate;
     a.tiles_m = cdiv(M, GBM); a.tiles_n = cdiv(N, GBN);
+    // few output tiles but a long contraction (the dgrads: 72 tiles x 94 K blocks): split K in two so
+    // that ~all SMs work; two partials added into a zeroed C are order-independent (a+b == b+a)
+    a.splits = 1;
+    if (a.tiles_m * a.tiles_n * 2 <= tc_num_sms() && cdiv(K, GBK) >= 8 && ldc == N) {
+        a.splits = 2;
+        if (!accumulate) ZRB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));
+    }
     if (!a_mn && !b_mn) return launch_gemm<false, false>(ta, tb, a, s);
     if (!a_mn && b_mn) return launch_gemm<false, true>(ta, tb, a, s);
     if (a_mn && !b_mn) return launch_gemm<true, false>(ta, tb, a, s);

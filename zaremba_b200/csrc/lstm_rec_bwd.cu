@@ -75,15 +75,16 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     const int ldd = Bp + 1;
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;
-    float* sD = (float*)(sB + b_bytes);  // [64][Bp+1] this CTA's partial product
-    uint64_t* bars = (uint64_t*)((uint8_t*)sD + 64 * ldd * 4);
+    float* sD = (float*)(sB + b_bytes);  // [2][64][Bp+1] this CTA's partial product (one buffer per accumulator)
+    uint64_t* bars = (uint64_t*)((uint8_t*)sD + 2 * 64 * ldd * 4);
     uint64_t* bar_a = bars;
-    uint64_t* bar_b = bars + 1;
-    uint64_t* bar_mma = bars + 2;
-    uint64_t* bar_part = bars + 3;  // 4 arrivals per step: every CTA of the cluster staged its partial
-    uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+    uint64_t* bar_b = bars + 1;                    // [kRecPieces]
+    uint64_t* bar_mma = bars + 1 + kRecPieces;
+    uint64_t* bar_part = bar_mma + 1;              // 4 arrivals per step: every CTA of the cluster staged its partial
+    uint32_t* tmem_slot = (uint32_t*)(bar_part + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster = blockIdx.x >> 2;
     const int UC = 4 * a.U;
@@ -91,59 +92,74 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     const int j0 = jc0 + (int)rank * a.U;    // first unit whose cell math this CTA owns
     const int nu = max(0, min(a.U, a.H - j0));
     const int T = a.T, B = a.B, H = a.H;
+    const int ksteps = a.Kc / 2;
+    const int piece_steps = (ksteps + kRecPieces - 1) / kRecPieces;
+    const bool tr = a.trace != nullptr && blockIdx.x == 0;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_a, 1); mbar_init(bar_b, 1); mbar_init(bar_mma, 1); mbar_init(bar_part, 4);
+        mbar_init(bar_a, 1);
+        for (int i = 0; i < kRecPieces; ++i) mbar_init(&bar_b[i], 1);
+        mbar_init(bar_mma, kRecMmaWarps);
+        mbar_init(bar_part, 4);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc<32>(tmem_slot);
+    if (warp == kRecMmaWarp) tmem_alloc<kRecTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive
 
-    if (warp == 5 && lane == 0) {
+    if (warp == kRecLoadWarp && lane == 0) {
         // ===================== loader =====================
         const uint8_t* src = (const uint8_t*)a.w_img + ((size_t)cluster * 4 + rank) * a_bytes;
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
+        const int lbo_b = a.GB * 128;
         for (int s = 1; s < T; ++s) {
             const int t = T - 1 - s;                      // step being computed; needs dG_{t+1}
             grid_counter_wait(a.counter, (unsigned int)s * a.nCTA);
-            if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 0] = clock64();
+            if (tr) a.trace[s * 8 + 0] = clock64();
             fence_proxy_async_all();
-            mbar_expect_tx(bar_b, b_bytes);
             const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + rank) * b_bytes;
-            bulk_load_1d(sB, img, b_bytes, bar_b);
+            for (int pc = 0; pc < kRecPieces; ++pc) {
+                const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
+                if (k0 >= k1) { mbar_arrive(&bar_b[pc]); continue; }
+                const int off = k0 * 2 * lbo_b, bytes = (k1 - k0) * 2 * lbo_b;
+                mbar_expect_tx(&bar_b[pc], bytes);
+                bulk_load_1d(sB + off, img + off, bytes, &bar_b[pc]);
+            }
         }
-    } else if (warp == 4 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if (warp >= kRecMmaWarp && warp < kRecMmaWarp + kRecMmaWarps && lane == 0) {
+        // ===================== MMA issuers: issuer i takes K steps i, i+2, ... into accumulator i =====================
+        const int me = warp - kRecMmaWarp;
+        const uint32_t my_acc = tmem_d + me * 32;
         const uint32_t idesc = make_idesc_f16(64, Bp, 0, 0);
         const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
         const uint32_t lbo_a = a.G * 128, lbo_b = a.GB * 128;
         bounded_mbar_wait(bar_a, 0);
         for (int s = 1; s < T; ++s) {
-            bounded_mbar_wait(bar_b, (s - 1) & 1);
-            tcgen05_fence_after();
-            if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 1] = clock64();
-            const int ksteps = a.Kc / 2;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
-                uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
-                umma_f16(tmem_d, da, db, idesc, ks != 0 ? 1u : 0u);
+            for (int pc = 0; pc < kRecPieces; ++pc) {
+                bounded_mbar_wait(&bar_b[pc], (s - 1) & 1);
+                tcgen05_fence_after();
+                if (tr && pc == 0 && me == 0) a.trace[s * 8 + 1] = clock64();
+                const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
+                for (int ks = k0 + ((k0 ^ me) & 1); ks < k1; ks += kRecMmaWarps) {
+                    uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
+                    uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
+                    umma_f16(my_acc, da, db, idesc, ks >= kRecMmaWarps ? 1u : 0u);
+                }
             }
             umma_commit(bar_mma);
-            if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 2] = clock64();
+            if (tr && me == 0) a.trace[s * 8 + 2] = clock64();
         }
-    } else if (warp < 4) {
-        // ===================== epilogue: 128 threads, cells (u, b) of this CTA's U units =====================
-        const int tid = threadIdx.x;                   // 0..127
-        const int cells = a.U * Bp;
-        constexpr int kMaxCell = 4;                    // U <= 16, Bp <= 32 -> <= 512 cells / 128 threads
-        float dcreg[kMaxCell];
+    } else if (warp < kRecEpiWarps) {
+        // ===================== epilogue: 256 threads, cells (u, b) of this CTA's U units =====================
+        const int tid = threadIdx.x;
+        const int cells = a.U * B;                     // cell = b * U + u (u fastest: contiguous j)
+        float dcreg[kRecMaxCell];
 #pragma unroll
-        for (int k = 0; k < kMaxCell; ++k) dcreg[k] = 0.f;
+        for (int k = 0; k < kRecMaxCell; ++k) dcreg[k] = 0.f;
         const uint64_t n_total = (uint64_t)T * B * H;
         const uint32_t sD_addr = smem_u32(sD);
         uint32_t part_addr[4];
@@ -151,16 +167,19 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         for (int rr = 0; rr < 4; ++rr) part_addr[rr] = mapa_shared(sD_addr, rr);
         const uint32_t bar_part_addr = smem_u32(bar_part);
         const float inv = 1.f / kGradScale;
+        const int quad = warp & 3, half = warp >> 2;
+        const size_t img_gate = (size_t)a.Kc * a.GB * 64;
 
         for (int s = 0; s < T; ++s) {
             const int t = T - 1 - s;
             // prefetch this step's saved activations and upstream gradient
-            float gi[kMaxCell], gf[kMaxCell], gg[kMaxCell], go[kMaxCell], ct[kMaxCell], cp[kMaxCell], dyv[kMaxCell];
+            float gi[kRecMaxCell], gf[kRecMaxCell], gg[kRecMaxCell], go[kRecMaxCell], ct[kRecMaxCell], cp[kRecMaxCell],
+                dyv[kRecMaxCell];
 #pragma unroll
-            for (int k = 0; k < kMaxCell; ++k) {
-                int cell = tid + 128 * k;
-                int u = cell / Bp, b = cell % Bp;
-                bool ok = cell < cells && u < nu && b < B;
+            for (int k = 0; k < kRecMaxCell; ++k) {
+                int cell = tid + kRecEpiThreads * k;
+                int b = cell / a.U, u = cell % a.U;
+                bool ok = cell < cells && u < nu;
                 gi[k] = gf[k] = gg[k] = go[k] = ct[k] = cp[k] = dyv[k] = 0.f;
                 if (ok) {
                     const int j = j0 + u;
@@ -176,20 +195,24 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             if (s > 0) {
                 bounded_mbar_wait(bar_mma, (s - 1) & 1);
                 tcgen05_fence_after();
-                if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 3] = clock64();
+                if (tr && tid == 0) a.trace[s * 8 + 3] = clock64();
                 // TMEM -> own shared staging: accumulator row i (cluster-local unit) in lane (i%16)+32*(i/16)
-                for (int c0 = 0; c0 < Bp; c0 += 8) {
-                    uint32_t v[8];
-                    tmem_ld_32x8(tmem_d + ((uint32_t)(32 * warp) << 16) + c0, v);
-                    tmem_ld_wait();
-                    if (lane < 16) {
+                {   // warp (quad, half): TMEM lanes [32*quad, +32) of accumulator `half` -> staging buffer `half`
+                    const bool used = half < ksteps;   // an issuer with no K step leaves its accumulator unwritten
+                    for (int c0 = 0; c0 < Bp; c0 += 8) {
+                        uint32_t v[8];
+                        tmem_ld_32x8(tmem_d + ((uint32_t)(32 * quad) << 16) + half * 32 + c0, v);
+                        tmem_ld_wait();
+                        if (lane < 16) {
+                            float* dst = sD + (half * 64 + 16 * quad + lane) * ldd + c0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) sD[(16 * warp + lane) * ldd + c0 + i] = __uint_as_float(v[i]);
+                            for (int i = 0; i < 8; ++i) dst[i] = used ? __uint_as_float(v[i]) : 0.f;
+                        }
                     }
                 }
                 tcgen05_fence_before();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 4] = clock64();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
                 if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
                 {   // wait until all four CTAs of the cluster staged their partials
                     uint32_t n = 0; long long t0 = 0;
@@ -202,21 +225,25 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     }
                 }
             }
-            if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 5] = clock64();
+            if (tr && tid == 0) a.trace[s * 8 + 5] = clock64();
+            __half hv[kRecMaxCell][4];
 #pragma unroll
-            for (int k = 0; k < kMaxCell; ++k) {
-                int cell = tid + 128 * k;
-                int u = cell / Bp, b = cell % Bp;
-                bool ok = cell < cells && u < nu && b < B;
+            for (int k = 0; k < kRecMaxCell; ++k) {
+                int cell = tid + kRecEpiThreads * k;
+                int b = cell / a.U, u = cell % a.U;
+                bool ok = cell < cells && u < nu;
                 if (!ok) continue;
                 float dh = dyv[k];
                 if (s > 0) {
                     const uint32_t off = (uint32_t)(((int)rank * a.U + u) * ldd + b) * 4u;
-                    float r = ld_dsmem_f32(part_addr[0] + off) + ld_dsmem_f32(part_addr[1] + off) +
-                              ld_dsmem_f32(part_addr[2] + off) + ld_dsmem_f32(part_addr[3] + off);
+                    const uint32_t off2 = off + (uint32_t)(64 * ldd) * 4u;
+                    float r = (ld_dsmem_f32(part_addr[0] + off) + ld_dsmem_f32(part_addr[0] + off2)) +
+                              (ld_dsmem_f32(part_addr[1] + off) + ld_dsmem_f32(part_addr[1] + off2)) +
+                              (ld_dsmem_f32(part_addr[2] + off) + ld_dsmem_f32(part_addr[2] + off2)) +
+                              (ld_dsmem_f32(part_addr[3] + off) + ld_dsmem_f32(part_addr[3] + off2));
                     dh += r * inv;
                 }
-                const float tc = tanhf(ct[k]);
+                const float tc = fast_tanh(ct[k]);
                 const float d_o = dh * tc;
                 const float dcc = dcreg[k] + dh * go[k] * (1.f - tc * tc);
                 const float d_i = dcc * gg[k], d_g = dcc * gi[k], d_f = dcc * cp[k];
@@ -227,32 +254,41 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 dg4[2] = d_g * (1.f - gg[k] * gg[k]);
                 dg4[3] = d_o * go[k] * (1.f - go[k]);
                 const int j = j0 + u;
-                const size_t n = (size_t)t * B + b;
-                __half* hrow = a.dG_h + n * a.G4p + j;
-                __half* img = a.g_img + (size_t)(t & 1) * 4 * ((size_t)a.Kc * a.GB * 64) +
-                              ((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7);
+                // critical path: the four gate images the next step multiplies with
+                __half* img = a.g_img + (size_t)(t & 1) * 4 * img_gate + ((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 +
+                              (b & 7) * 8 + (j & 7);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float v = fminf(fmaxf(dg4[q] * kGradScale, -65504.f), 65504.f);
-                    __half hv = __float2half_rn(v);
-                    hrow[(size_t)q * H] = hv;
-                    img[(size_t)q * ((size_t)a.Kc * a.GB * 64)] = hv;
+                    hv[k][q] = __float2half_rn(v);
+                    img[(size_t)q * img_gate] = hv[k][q];
                 }
             }
-            if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[s * 8 + 6] = clock64();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tr && tid == 0) a.trace[s * 8 + 6] = clock64();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
                 __threadfence();
                 fence_proxy_async_all();
                 atomicAdd(a.counter, 1u);
-                if (a.trace && blockIdx.x == 0) a.trace[s * 8 + 7] = clock64();
+                if (tr) a.trace[s * 8 + 7] = clock64();
+            }
+            // off the critical path: row-major image for the batched dgrad / wgrad GEMMs
+#pragma unroll
+            for (int k = 0; k < kRecMaxCell; ++k) {
+                int cell = tid + kRecEpiThreads * k;
+                int b = cell / a.U, u = cell % a.U;
+                bool ok = cell < cells && u < nu;
+                if (!ok) continue;
+                __half* hrow = a.dG_h + ((size_t)t * B + b) * a.G4p + j0 + u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hrow[(size_t)q * H] = hv[k][q];
             }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    if (warp == 4) tmem_dealloc<32>(tmem_d);
+    if (warp == kRecMmaWarp) tmem_dealloc<kRecTmemCols>(tmem_d);
     cluster_sync_all();   // no CTA leaves while a peer may still read its staged partial
 }
 
@@ -296,9 +332,8 @@ int rec_bwd_plan(int H, int B, RecPlan* plan) {
         int ncl = (H + UC - 1) / UC;
         if (ncl > max_clusters) break;
         int G = UC / 8;
-        size_t smem = (size_t)plan->Kc * G * 128 + (size_t)plan->Kc * plan->GB * 128 + 64 * (plan->GB * 8 + 1) * 4 +
-                      64 + 256;
-        if (smem <= 227 * 1024) {
+        size_t smem = rec_smem_bytes(plan->Kc, G, plan->GB);
+        if (smem <= 227 * 1024 && U * B <= kRecMaxCell * kRecEpiThreads) {
             plan->U = U; plan->G = G; plan->nCTA = ncl * 4; plan->smem = (int)smem; plan->ok = 1;
             return ZRB_OK;
         }

@@ -8,20 +8,23 @@
 // registers of the epilogue threads for the whole window.
 //
 // Per step:
-//   loader thread   waits on the grid barrier counter (acquire), then ONE cp.async.bulk brings the
-//                   72 KB h_{t-1} operand image (written by all CTAs, already in UMMA layout) into
-//                   shared memory
-//   MMA thread      H/16 tcgen05.mma (M=64, N=pad8(B), K=16): D[4U x B] in TMEM, commit -> mbarrier
-//   epilogue warps  tcgen05.ld D, add the prefetched XG slice, sigmoid/tanh, c/h update, dropout;
-//                   write activated gates + c_t (for backward), h_t as fp16 into (a) the next step's
-//                   operand image, (b) the row-major image the wgrad GEMM reads, (c) dropout(h_t) for
-//                   the next layer; then arrive on the grid barrier (release)
+//   loader thread   waits on the grid barrier counter (acquire), then brings the 72 KB h_{t-1}
+//                   operand image (written by all CTAs, already in UMMA layout) into shared memory
+//                   as four cp.async.bulk pieces, each with its own mbarrier, so the MMAs start when
+//                   the first quarter of K has landed
+//   2 MMA threads   H/16 tcgen05.mma (M=64, N=pad8(B), K=16), even K steps by one thread into TMEM
+//                   accumulator 0, odd steps by another into accumulator 1.  tcgen05.mma has a ~45 clk
+//                   floor per instruction for any N <= 64 (profiles/r01_tcgen05_mma_issue_microbench.csv),
+//                   i.e. >= 4200 clk per step; a single issuing thread reaches only ~90 clk per MMA
+//   8 epilogue warps drain both accumulators through shared memory, add the x-part
+//                   pre-activations prefetched during the MMAs, apply sigmoid/tanh/cell update/dropout.
+//                   The next step's operand image is stored FIRST and published (fence + grid-barrier
+//                   arrival); everything backward needs (activated gates, c_t, row-major fp16 h,
+//                   dropout(h) for the next layer) is stored after the arrival, off the critical path.
 //
-// Roofline: latency/L2 bound, not tensor bound -- per step each CTA streams its 144 KB weight slice
-// from shared memory through the tensor core (>= 1150 clk at 128 B/clk) and all CTAs re-read the
-// 72 KB h image from L2; algorithmic flops per layer call = 8*T*B*H^2.
-#include <cooperative_groups.h>
-
+// Roofline: latency/L2/shared-memory bound, not tensor bound -- per step each CTA streams its 144 KB
+// weight slice from shared memory through the tensor core (>= 1150 clk at 128 B/clk) and all CTAs
+// re-read the 72 KB h image from L2; algorithmic flops per layer call = 8*T*B*H^2.
 #include "rec_common.cuh"
 
 namespace zrb {
@@ -48,160 +51,185 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     const int a_bytes = a.Kc * a.G * 128;
     const int b_bytes = a.Kc * a.GB * 128;
     const int Bp = a.GB * 8;
+    const int ldd = Bp + 1;
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;
-    float* sD = (float*)(sB + b_bytes);                       // [64][Bp+1] staging of the accumulator
-    uint64_t* bars = (uint64_t*)((uint8_t*)sD + 64 * (Bp + 1) * 4);
+    float* sD = (float*)(sB + b_bytes);                       // [2][64][Bp+1] accumulator staging
+    uint64_t* bars = (uint64_t*)((uint8_t*)sD + 2 * 64 * ldd * 4);
     uint64_t* bar_a = bars;        // weight slice landed
-    uint64_t* bar_b = bars + 1;    // h image of this step landed
-    uint64_t* bar_mma = bars + 2;  // accumulator ready
-    uint32_t* tmem_slot = (uint32_t*)(bars + 3);
+    uint64_t* bar_b = bars + 1;    // [kRecPieces] h image pieces of this step landed
+    uint64_t* bar_mma = bars + 1 + kRecPieces;  // accumulators ready
+    uint32_t* tmem_slot = (uint32_t*)(bar_mma + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
     const int j0 = cta * a.U;
     const int nu = min(a.U, a.H - j0);
+    const int ksteps = a.Kc / 2;
+    const int piece_steps = (ksteps + kRecPieces - 1) / kRecPieces;
+    const bool tr = a.trace != nullptr && cta == 0;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_a, 1); mbar_init(bar_b, 1); mbar_init(bar_mma, 1);
+        mbar_init(bar_a, 1);
+        for (int i = 0; i < kRecPieces; ++i) mbar_init(&bar_b[i], 1);
+        mbar_init(bar_mma, kRecMmaWarps);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc<32>(tmem_slot);
+    if (warp == kRecMmaWarp) tmem_alloc<kRecTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == 5 && lane == 0) {
+    if (warp == kRecLoadWarp && lane == 0) {
         // ===================== loader =====================
         const uint8_t* src = (const uint8_t*)a.w_img + (size_t)cta * a_bytes;
         mbar_expect_tx(bar_a, a_bytes);
-        for (int off = 0; off < a_bytes; off += 32768) {
-            int n = min(32768, a_bytes - off);
-            bulk_load_1d(sA + off, src + off, n, bar_a);
-        }
+        for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
+        const int lbo_b = a.GB * 128;
         for (int t = 0; t < a.T; ++t) {
-            if (t > 0) {
-                grid_counter_wait(a.counter, (unsigned int)t * a.nCTA);
-            }
-            if (a.trace && cta == 0) a.trace[t * 8 + 0] = clock64();
+            if (t > 0) grid_counter_wait(a.counter, (unsigned int)t * a.nCTA);
+            if (tr) a.trace[t * 8 + 0] = clock64();
             fence_proxy_async_all();
-            mbar_expect_tx(bar_b, b_bytes);
-            bulk_load_1d(sB, (const uint8_t*)a.h_img + (size_t)t * b_bytes, b_bytes, bar_b);
+            const uint8_t* img = (const uint8_t*)a.h_img + (size_t)t * b_bytes;
+            for (int pc = 0; pc < kRecPieces; ++pc) {
+                const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
+                if (k0 >= k1) { mbar_arrive(&bar_b[pc]); continue; }
+                const int off = k0 * 2 * lbo_b, bytes = (k1 - k0) * 2 * lbo_b;
+                mbar_expect_tx(&bar_b[pc], bytes);
+                bulk_load_1d(sB + off, img + off, bytes, &bar_b[pc]);
+            }
         }
-    } else if (warp == 4 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if (warp >= kRecMmaWarp && warp < kRecMmaWarp + kRecMmaWarps && lane == 0) {
+        // ===================== MMA issuers: issuer i takes K steps i, i+2, ... into accumulator i =====================
+        const int me = warp - kRecMmaWarp;
+        const uint32_t my_acc = tmem_d + me * 32;
         const uint32_t idesc = make_idesc_f16(64, Bp, 0, 0);
         const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
         const uint32_t lbo_a = a.G * 128, lbo_b = a.GB * 128;
         bounded_mbar_wait(bar_a, 0);
         for (int t = 0; t < a.T; ++t) {
-            bounded_mbar_wait(bar_b, t & 1);
-            tcgen05_fence_after();
-            if (a.trace && cta == 0) a.trace[t * 8 + 1] = clock64();
-            const int ksteps = a.Kc / 2;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
-                uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
-                umma_f16(tmem_d, da, db, idesc, ks != 0 ? 1u : 0u);
+            for (int pc = 0; pc < kRecPieces; ++pc) {
+                bounded_mbar_wait(&bar_b[pc], t & 1);
+                tcgen05_fence_after();
+                if (tr && pc == 0 && me == 0) a.trace[t * 8 + 1] = clock64();
+                const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
+                for (int ks = k0 + ((k0 ^ me) & 1); ks < k1; ks += kRecMmaWarps) {
+                    uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
+                    uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
+                    umma_f16(my_acc, da, db, idesc, ks >= kRecMmaWarps ? 1u : 0u);
+                }
             }
             umma_commit(bar_mma);
-            if (a.trace && cta == 0) a.trace[t * 8 + 2] = clock64();
+            if (tr && me == 0) a.trace[t * 8 + 2] = clock64();
         }
-    } else if (warp < 4) {
-        // ===================== epilogue =====================
-        // accumulator row i = 4*u + q lives in TMEM lane (i % 16) + 32 * (i / 16): this warp holds
-        // units u = 4*warp .. 4*warp+3 in its lanes 0..15.  Cells (u, b) are dealt to the 32 lanes.
-        const int cells = 4 * Bp;
-        const int ncell = (cells + 31) / 32;      // <= 4 (Bp <= 32)
-        float creg[4];
+    } else if (warp < kRecEpiWarps) {
+        // ===================== epilogue: 256 threads =====================
+        const int tid = threadIdx.x;
         const int B = a.B, H = a.H;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            creg[k] = 0.f;
-            int cell = lane + 32 * k;
-            if (k < ncell && cell < cells) {
-                int ul = cell / Bp, b = cell % Bp, u = 4 * warp + ul;
-                if (u < nu && b < B) creg[k] = a.c0[(size_t)b * H + j0 + u];
-            }
-        }
+        const int cells = a.U * B;                     // cell = b * U + u (u fastest: contiguous j)
         const uint64_t n_total = (uint64_t)a.T * B * H;
+        float creg[kRecMaxCell];
+#pragma unroll
+        for (int k = 0; k < kRecMaxCell; ++k) {
+            int cell = tid + kRecEpiThreads * k;
+            int b = cell / a.U, u = cell % a.U;
+            creg[k] = (cell < cells && u < nu) ? a.c0[(size_t)b * H + j0 + u] : 0.f;
+        }
+        const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant / which accumulator pair
         for (int t = 0; t < a.T; ++t) {
             // prefetch the x-part pre-activations of this step while the MMAs run
-            float pre[4][4];
+            float pre[kRecMaxCell][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int cell = lane + 32 * k;
-                int ul = cell / Bp, b = cell % Bp, u = 4 * warp + ul;
-                bool ok = k < ncell && cell < cells && u < nu && b < B;
+            for (int k = 0; k < kRecMaxCell; ++k) {
+                int cell = tid + kRecEpiThreads * k;
+                int b = cell / a.U, u = cell % a.U;
+                bool ok = cell < cells && u < nu;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     pre[k][q] = ok ? __ldg(a.gates + ((size_t)t * B + b) * 4 * H + (size_t)q * H + j0 + u) : 0.f;
             }
             bounded_mbar_wait(bar_mma, t & 1);
             tcgen05_fence_after();
-            if (a.trace && cta == 0 && threadIdx.x == 0) a.trace[t * 8 + 3] = clock64();
-            // TMEM -> registers -> shared staging (rows 16*warp .. 16*warp+15 belong to this warp)
-            for (int c0 = 0; c0 < Bp; c0 += 8) {
-                uint32_t v[8];
-                tmem_ld_32x8(tmem_d + ((uint32_t)(32 * warp) << 16) + c0, v);
-                tmem_ld_wait();
-                if (lane < 16) {
+            if (tr && tid == 0) a.trace[t * 8 + 3] = clock64();
+            // drain: warp (quad, half) sums accumulators 2*half, 2*half+1 of TMEM lanes [32*quad, +32)
+            // into staging buffer `half`; accumulator row i sits in lane (i % 16) + 32 * (i / 16)
+            {   // warp (quad, half): TMEM lanes [32*quad, +32) of accumulator `half` -> staging buffer `half`
+                const bool used = half < ksteps;   // an issuer with no K step leaves its accumulator unwritten
+                for (int c0 = 0; c0 < Bp; c0 += 8) {
+                    uint32_t v[8];
+                    tmem_ld_32x8(tmem_d + ((uint32_t)(32 * quad) << 16) + half * 32 + c0, v);
+                    tmem_ld_wait();
+                    if (lane < 16) {
+                        float* dst = sD + (half * 64 + 16 * quad + lane) * ldd + c0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) sD[(16 * warp + lane) * (Bp + 1) + c0 + i] = __uint_as_float(v[i]);
+                        for (int i = 0; i < 8; ++i) dst[i] = used ? __uint_as_float(v[i]) : 0.f;
+                    }
                 }
             }
             tcgen05_fence_before();
-            __syncwarp();
-            if (a.trace && cta == 0 && threadIdx.x == 0) a.trace[t * 8 + 4] = clock64();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tr && tid == 0) a.trace[t * 8 + 4] = clock64();
+            float o_i[kRecMaxCell], o_f[kRecMaxCell], o_g[kRecMaxCell], o_o[kRecMaxCell], o_h[kRecMaxCell];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int cell = lane + 32 * k;
-                int ul = cell / Bp, b = cell % Bp, u = 4 * warp + ul;
-                bool ok = k < ncell && cell < cells && u < nu && b < B;
+            for (int k = 0; k < kRecMaxCell; ++k) {
+                int cell = tid + kRecEpiThreads * k;
+                int b = cell / a.U, u = cell % a.U;
+                bool ok = cell < cells && u < nu;
+                o_i[k] = o_f[k] = o_g[k] = o_o[k] = o_h[k] = 0.f;
                 if (!ok) continue;
-                const float* d = sD + (16 * warp + 4 * ul) * (Bp + 1) + b;
-                float zi = pre[k][0] + d[0];
-                float zf = pre[k][1] + d[Bp + 1];
-                float zg = pre[k][2] + d[2 * (Bp + 1)];
-                float zo = pre[k][3] + d[3 * (Bp + 1)];
-                float gi = sigmoidf_(zi), gf = sigmoidf_(zf), gg = tanhf(zg), go = sigmoidf_(zo);
+                const float* d0 = sD + (4 * u) * ldd + b;
+                const float* d1 = d0 + 64 * ldd;
+                float zi = pre[k][0] + (d0[0] + d1[0]);
+                float zf = pre[k][1] + (d0[ldd] + d1[ldd]);
+                float zg = pre[k][2] + (d0[2 * ldd] + d1[2 * ldd]);
+                float zo = pre[k][3] + (d0[3 * ldd] + d1[3 * ldd]);
+                float gi = fast_sigmoid(zi), gf = fast_sigmoid(zf), gg = fast_tanh(zg), go = fast_sigmoid(zo);
                 float c = gf * creg[k] + gi * gg;
-                float h = go * tanhf(c);
+                float h = go * fast_tanh(c);
                 creg[k] = c;
+                o_i[k] = gi; o_f[k] = gf; o_g[k] = gg; o_o[k] = go; o_h[k] = h;
+                // critical path: the next step's operand image [kc][g][r][e], kc = j/8, e = j%8, g = b/8, r = b%8
                 const int j = j0 + u;
-                const size_t n = (size_t)t * B + b;
-                float* grow = a.gates + n * 4 * H + j;
-                grow[0] = gi; grow[H] = gf; grow[2 * (size_t)H] = gg; grow[3 * (size_t)H] = go;
-                a.cst[n * H + j] = c;
-                __half hh = __float2half_rn(h);
-                // next step's operand image: [kc][g][r][e], kc = j/8, e = j%8, g = b/8, r = b%8
                 __half* img = a.h_img + (size_t)(t + 1) * ((size_t)a.Kc * a.GB * 64);
-                img[((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7)] = hh;
-                a.hprev_h[((size_t)B + n) * a.Hp + j] = hh;
-                float y = h * mask_mul1(a.m, (uint64_t)n * H + j, n_total);
-                a.y_h[n * a.Hp + j] = __float2half_rn(y);
-                if (t == a.T - 1) {
-                    if (a.h_last) a.h_last[(size_t)b * H + j] = h;
-                    if (a.c_last) a.c_last[(size_t)b * H + j] = c;
-                }
+                img[((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7)] = __float2half_rn(h);
             }
-            // publish: all epilogue threads' global writes -> grid barrier arrival
-            if (a.trace && cta == 0 && threadIdx.x == 0) a.trace[t * 8 + 5] = clock64();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 0) {
-                if (a.trace && cta == 0) a.trace[t * 8 + 6] = clock64();
+            if (tr && tid == 0) a.trace[t * 8 + 5] = clock64();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid == 0) {
+                if (tr) a.trace[t * 8 + 6] = clock64();
                 __threadfence();
                 fence_proxy_async_all();
                 atomicAdd(a.counter, 1u);
-                if (a.trace && cta == 0) a.trace[t * 8 + 7] = clock64();
+                if (tr) a.trace[t * 8 + 7] = clock64();
+            }
+            // off the critical path: what backward and the next layer read after this kernel
+#pragma unroll
+            for (int k = 0; k < kRecMaxCell; ++k) {
+                int cell = tid + kRecEpiThreads * k;
+                int b = cell / a.U, u = cell % a.U;
+                bool ok = cell < cells && u < nu;
+                if (!ok) continue;
+                const int j = j0 + u;
+                const size_t n = (size_t)t * B + b;
+                float* grow = a.gates + n * 4 * H + j;
+                grow[0] = o_i[k]; grow[H] = o_f[k]; grow[2 * (size_t)H] = o_g[k]; grow[3 * (size_t)H] = o_o[k];
+                a.cst[n * H + j] = creg[k];
+                a.hprev_h[((size_t)B + n) * a.Hp + j] = __float2half_rn(o_h[k]);
+                float y = o_h[k] * mask_mul1(a.m, (uint64_t)n * H + j, n_total);
+                a.y_h[n * a.Hp + j] = __float2half_rn(y);
+                if (t == a.T - 1) {
+                    if (a.h_last) a.h_last[(size_t)b * H + j] = o_h[k];
+                    if (a.c_last) a.c_last[(size_t)b * H + j] = creg[k];
+                }
             }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    if (warp == 4) tmem_dealloc<32>(tmem_d);
+    if (warp == kRecMmaWarp) tmem_dealloc<kRecTmemCols>(tmem_d);
 }
 
 // ---- weight / state image builders ---------------------------------------------------------------
@@ -236,22 +264,25 @@ __global__ void pack_h_image_kernel(const float* __restrict__ h, __half* __restr
 }
 
 // ---- host ------------------------------------------------------------------------------------------
+size_t rec_smem_bytes(int Kc, int G, int GB) {
+    return (size_t)Kc * G * 128 + (size_t)Kc * GB * 128 + 2 * 64 * (GB * 8 + 1) * 4 + 128 /*align*/ + 128 /*bars*/;
+}
+
 int rec_fwd_plan(int H, int B, RecPlan* plan) {
     int nsm = tc_num_sms();
     int Kp = (H + 15) / 16 * 16;
     plan->Kc = Kp / 8;
     plan->GB = (B + 7) / 8;
     plan->ok = 0;
-    if (plan->GB * 8 > 32) return ZRB_OK;  // TMEM allocation / staging sized for N <= 32
+    if (plan->GB * 8 > 32) return ZRB_OK;  // TMEM accumulators / staging sized for N <= 32
     for (int U = 16; U >= 1; --U) {
         int n = (H + U - 1) / U;
         if (n > nsm) break;
         int G = (4 * U + 7) / 8;
-        size_t smem = (size_t)plan->Kc * G * 128 + (size_t)plan->Kc * plan->GB * 128 +
-                      64 * (plan->GB * 8 + 1) * 4 + 64 + 256;
+        size_t smem = rec_smem_bytes(plan->Kc, G, plan->GB);
         // the M=64 atom reads 8 row groups per K chunk: the last chunk reaches (8-G)*128 B past the
-        // slice, which must still be inside the allocation (it lands in the h image buffer)
-        if (smem <= 227 * 1024 && (8 - G) * 128 <= plan->Kc * plan->GB * 128) {
+        // slice, which lands in the h image buffer that follows it
+        if (smem <= 227 * 1024 && U * B <= kRecMaxCell * kRecEpiThreads) {
             plan->U = U; plan->G = G; plan->nCTA = n; plan->smem = (int)smem; plan->ok = 1;
             return ZRB_OK;
         }
@@ -283,7 +314,8 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, __half* h_img, float* ga
     RecFwdArgs a;
     a.w_img = w_img; a.h_img = h_img; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;
     a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter;
-    a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
+    a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
+    a.trace = trace;
     void* args[] = {&a};
     ZRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_kernel, dim3(p.nCTA), dim3(kRecThreads), args,
                                          (size_t)p.smem, s));

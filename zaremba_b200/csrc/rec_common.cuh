@@ -6,7 +6,18 @@
 namespace zrb {
 using namespace tc;
 
-constexpr int kRecThreads = 192;  // warps 0-3 epilogue, warp 4 MMA + TMEM, warp 5 loader
+constexpr int kRecEpiWarps = 8;                       // warps 0-7: accumulator drain + cell math
+constexpr int kRecEpiThreads = kRecEpiWarps * 32;
+constexpr int kRecMmaWarp = 8;                        // warps 8 and 9: lane 0 of each issues every other tcgen05.mma into
+constexpr int kRecMmaWarps = 2;                       //   its OWN accumulator (warp 8 also owns the TMEM allocation)
+constexpr int kRecLoadWarp = 10;                      // lane 0: grid-barrier wait + bulk copies
+constexpr int kRecThreads = 352;
+constexpr int kRecTmemCols = 64;                      // two fp32 accumulators, N <= 32 columns each.  tcgen05.mma has a
+                                                      // ~45 clk floor per instruction for N <= 64 (measured); one issuing
+                                                      // thread only reaches ~90 clk (descriptor math + R2UR in series with
+                                                      // the issue), two threads with private accumulators reach the floor
+constexpr int kRecPieces = 4;                         // operand image arrives in this many bulk copies
+constexpr int kRecMaxCell = 2;                        // (unit, batch) cells per epilogue thread
 constexpr long long kSpinCycles = 6000000000ll;  // ~3 s at 2 GHz: a lost wake-up traps instead of hanging the GPU
 
 __device__ __forceinline__ void bounded_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -27,6 +38,10 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     return v;
 }
 
+
+// sigmoid / tanh on the SFU exp path (abs error ~1e-7, far below the fp16 operand noise of this engine)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // spin on a global counter (grid barrier) with acquire semantics and the same bounded wait
 __device__ __forceinline__ void grid_counter_wait(const unsigned int* counter, unsigned int target) {

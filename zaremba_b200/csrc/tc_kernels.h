@@ -29,6 +29,7 @@ struct RecPlan {
     int nCTA;
     int smem;
 };
+size_t rec_smem_bytes(int Kc, int G, int GB);
 int rec_fwd_plan(int H, int B, RecPlan* plan);
 int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s);
 int pack_h_image(const float* h, __half* img, int B, int H, const RecPlan& p, cudaStream_t s);
