@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
 }
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
     float v;
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
     return v;
 }
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 tcgen05_fence_after();
                 if (tr && pc == 0 && me == 0) a.trace[s * 8 + 1] = clock64();
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
-                for (int ks = k0 + ((k0 ^ me) & 1); ks < k1; ks += kRecMmaWarps) {
+                for (int ks = k0 + ((me - k0) & (kRecMmaWarps - 1)); ks < k1; ks += kRecMmaWarps) {
                     uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
                     uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
                     umma_f16(my_acc, da, db, idesc, ks >= kRecMmaWarps ? 1u : 0u);
@@ -197,16 +197,19 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 tcgen05_fence_after();
                 if (tr && tid == 0) a.trace[s * 8 + 3] = clock64();
                 // TMEM -> own shared staging: accumulator row i (cluster-local unit) in lane (i%16)+32*(i/16)
-                {   // warp (quad, half): TMEM lanes [32*quad, +32) of accumulator `half` -> staging buffer `half`
-                    const bool used = half < ksteps;   // an issuer with no K step leaves its accumulator unwritten
+                {   // warp (quad, half): TMEM lanes [32*quad, +32), accumulators half and half+2 summed -> staging buffer `half`
+                    const bool u0 = half < ksteps, u1 = half + 2 < ksteps;   // an issuer with no K step leaves its accumulator unwritten
                     for (int c0 = 0; c0 < Bp; c0 += 8) {
-                        uint32_t v[8];
-                        tmem_ld_32x8(tmem_d + ((uint32_t)(32 * quad) << 16) + half * 32 + c0, v);
+                        uint32_t v0[8], v1[8];
+                        const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
+                        tmem_ld_32x8(base + half * 32, v0);
+                        tmem_ld_32x8(base + (half + 2) * 32, v1);
                         tmem_ld_wait();
                         if (lane < 16) {
                             float* dst = sD + (half * 64 + 16 * quad + lane) * ldd + c0;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) dst[i] = used ? __uint_as_float(v[i]) : 0.f;
+                            for (int i = 0; i < 8; ++i)
+                                dst[i] = (u0 ? __uint_as_float(v0[i]) : 0.f) + (u1 ? __uint_as_float(v1[i]) : 0.f);
                         }
                     }
                 }
@@ -237,10 +240,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 if (s > 0) {
                     const uint32_t off = (uint32_t)(((int)rank * a.U + u) * ldd + b) * 4u;
                     const uint32_t off2 = off + (uint32_t)(64 * ldd) * 4u;
-                    float r = (ld_dsmem_f32(part_addr[0] + off) + ld_dsmem_f32(part_addr[0] + off2)) +
-                              (ld_dsmem_f32(part_addr[1] + off) + ld_dsmem_f32(part_addr[1] + off2)) +
-                              (ld_dsmem_f32(part_addr[2] + off) + ld_dsmem_f32(part_addr[2] + off2)) +
-                              (ld_dsmem_f32(part_addr[3] + off) + ld_dsmem_f32(part_addr[3] + off2));
+                    float pp[8];   // issue all eight DSMEM loads before the first use (each is ~200+ clk)
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        pp[2 * rr] = ld_dsmem_f32(part_addr[rr] + off);
+                        pp[2 * rr + 1] = ld_dsmem_f32(part_addr[rr] + off2);
+                    }
+                    float r = ((pp[0] + pp[1]) + (pp[2] + pp[3])) + ((pp[4] + pp[5]) + (pp[6] + pp[7]));
                     dh += r * inv;
                 }
                 const float tc = fast_tanh(ct[k]);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 tcgen05_fence_after();
                 if (tr && pc == 0 && me == 0) a.trace[t * 8 + 1] = clock64();
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
-                for (int ks = k0 + ((k0 ^ me) & 1); ks < k1; ks += kRecMmaWarps) {
+                for (int ks = k0 + ((me - k0) & (kRecMmaWarps - 1)); ks < k1; ks += kRecMmaWarps) {
                     uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
                     uint64_t db = make_smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128, kSwizzleNone);
                     umma_f16(my_acc, da, db, idesc, ks >= kRecMmaWarps ? 1u : 0u);
@@ -155,16 +155,19 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             if (tr && tid == 0) a.trace[t * 8 + 3] = clock64();
             // drain: warp (quad, half) sums accumulators 2*half, 2*half+1 of TMEM lanes [32*quad, +32)
             // into staging buffer `half`; accumulator row i sits in lane (i % 16) + 32 * (i / 16)
-            {   // warp (quad, half): TMEM lanes [32*quad, +32) of accumulator `half` -> staging buffer `half`
-                const bool used = half < ksteps;   // an issuer with no K step leaves its accumulator unwritten
+            {   // warp (quad, half): TMEM lanes [32*quad, +32), accumulators half and half+2 summed -> staging buffer `half`
+                const bool u0 = half < ksteps, u1 = half + 2 < ksteps;   // an issuer with no K step leaves its accumulator unwritten
                 for (int c0 = 0; c0 < Bp; c0 += 8) {
-                    uint32_t v[8];
-                    tmem_ld_32x8(tmem_d + ((uint32_t)(32 * quad) << 16) + half * 32 + c0, v);
+                    uint32_t v0[8], v1[8];
+                    const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
+                    tmem_ld_32x8(base + half * 32, v0);
+                    tmem_ld_32x8(base + (half + 2) * 32, v1);
                     tmem_ld_wait();
                     if (lane < 16) {
                         float* dst = sD + (half * 64 + 16 * quad + lane) * ldd + c0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = used ? __uint_as_float(v[i]) : 0.f;
+                        for (int i = 0; i < 8; ++i)
+                            dst[i] = (u0 ? __uint_as_float(v0[i]) : 0.f) + (u1 ? __uint_as_float(v1[i]) : 0.f);
                     }
                 }
             }

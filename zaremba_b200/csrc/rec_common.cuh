@@ -8,14 +8,14 @@ using namespace tc;
 
 constexpr int kRecEpiWarps = 8;                       // warps 0-7: accumulator drain + cell math
 constexpr int kRecEpiThreads = kRecEpiWarps * 32;
-constexpr int kRecMmaWarp = 8;                        // warps 8 and 9: lane 0 of each issues every other tcgen05.mma into
-constexpr int kRecMmaWarps = 2;                       //   its OWN accumulator (warp 8 also owns the TMEM allocation)
-constexpr int kRecLoadWarp = 10;                      // lane 0: grid-barrier wait + bulk copies
-constexpr int kRecThreads = 352;
-constexpr int kRecTmemCols = 64;                      // two fp32 accumulators, N <= 32 columns each.  tcgen05.mma has a
+constexpr int kRecMmaWarp = 8;                        // warps 8..11: lane 0 of warp 8+i issues K steps i, i+4, ... into its
+constexpr int kRecMmaWarps = 4;                       //   OWN accumulator i (warp 8 also owns the TMEM allocation)
+constexpr int kRecLoadWarp = 12;                      // lane 0: grid-barrier wait + bulk copies
+constexpr int kRecThreads = 416;
+constexpr int kRecTmemCols = 128;                     // four fp32 accumulators, N <= 32 columns each.  tcgen05.mma has a
                                                       // ~45 clk floor per instruction for N <= 64 (measured); one issuing
                                                       // thread only reaches ~90 clk (descriptor math + R2UR in series with
-                                                      // the issue), two threads with private accumulators reach the floor
+                                                      // the issue); 2 threads with private accumulators reach ~57, 4 threads the floor
 constexpr int kRecPieces = 4;                         // operand image arrives in this many bulk copies
 constexpr int kRecMaxCell = 2;                        // (unit, batch) cells per epilogue thread
 constexpr long long kSpinCycles = 6000000000ll;  // ~3 s at 2 GHz: a lost wake-up traps instead of hanging the GPU
