@@ -139,6 +139,16 @@ int  zrb_train_step_grads(zrb_ctx* ctx, const zrb_params* p, const zrb_params* g
                           const int64_t* x, const int64_t* y, int32_t T, int32_t B,
                           const zrb_states* in, const zrb_states* out,
                           uint64_t seed, uint64_t step, float* loss, void* stream);
+/* The same gradients in phases, so that a data-parallel caller can start reducing a bucket while
+ * the rest of backward still runs: after _begin (forward, loss, projection backward) the gradients of
+ * fc.W / fc.b are complete; after _layer(l), called for l = L-1 .. 0 in that order, those of layer l
+ * (and, for l = 0, of embed.W) are complete.  _begin + all _layer calls == zrb_train_step_grads. */
+int  zrb_train_step_begin(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,
+                          const int64_t* x, const int64_t* y, int32_t T, int32_t B,
+                          const zrb_states* in, const zrb_states* out,
+                          uint64_t seed, uint64_t step, float* loss, void* stream);
+int  zrb_train_step_layer(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads, int32_t layer,
+                          void* stream);
 int  zrb_train_step_update(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,
                            float lr, float max_norm, float* norm_out, void* stream);
 

@@ -349,3 +349,35 @@ def test_error_paths():
     cfg = _lib.ZrbConfig(0, 8, 1, 2, 2, 0, 0.0, 0)
     h = C.c_void_p()
     assert lib.zrb_ctx_create(C.byref(cfg), C.byref(h)) == -1
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_phased_backward_equals_monolithic(engine):
+    """zrb_train_step_begin + zrb_train_step_layer(L-1..0) produce the gradients of zrb_train_step_grads
+    (the data-parallel trainer reduces buckets between the phases); out-of-order layers are refused."""
+    import zaremba_b200
+    from zaremba_b200 import _lib
+    lib = _lib.load()
+    c = StepCase("mid_H72")
+    grads = []
+    for phased in (False, True):
+        m = _model_from_case(c, engine)
+        m.train()
+        tr = zaremba_b200.Trainer(m, c.B, c.T)
+        x = torch.tensor(c.x(0)).to(_dev()).contiguous()
+        y = torch.tensor(c.y(0)).to(_dev()).contiguous()
+        if not phased:
+            _lib.check(lib.zrb_train_step_grads(tr.ctx, C.byref(tr._ps), C.byref(tr._gs), _lib.ptr(x), _lib.ptr(y),
+                                                c.T, c.B, C.byref(tr._st), C.byref(tr._st), 1, 0, _lib.ptr(tr.loss), None))
+        else:
+            _lib.check(lib.zrb_train_step_begin(tr.ctx, C.byref(tr._ps), C.byref(tr._gs), _lib.ptr(x), _lib.ptr(y),
+                                                c.T, c.B, C.byref(tr._st), C.byref(tr._st), 1, 0, _lib.ptr(tr.loss), None))
+            assert lib.zrb_train_step_layer(tr.ctx, C.byref(tr._ps), C.byref(tr._gs), 0, None) == -3   # wrong order
+            for l in range(c.L - 1, -1, -1):
+                _lib.check(lib.zrb_train_step_layer(tr.ctx, C.byref(tr._ps), C.byref(tr._gs), l, None))
+        torch.cuda.synchronize()
+        grads.append(tr.flat_g.clone())
+        lo, hi = tr._buckets[0]
+        assert hi == tr.flat_g.numel() and tr._buckets[-1][0] == 0
+        assert sum(b - a for a, b in tr._buckets) == tr.flat_g.numel()
+    assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-7 * float(grads[0].abs().max()) + 1e-9)

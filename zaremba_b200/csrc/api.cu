@@ -240,6 +240,31 @@ int zrb_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, c
     return ZRB_OK;
 }
 
+// Phased variant of zrb_train_step_grads for overlapping the data-parallel all-reduce with backward.
+int zrb_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, const int64_t* x, const int64_t* y,
+                         int32_t T, int32_t B, const zrb_states* in, const zrb_states* out, uint64_t seed,
+                         uint64_t step, float* loss, void* stream) {
+    ZRB_REQUIRE(c && p && g && x && y && in && out, "null argument");
+    ZRB_TRY(check_shapes(c, T, B));
+    if (c->cfg.engine == ZRB_ENGINE_TC)
+        return tc_train_step_begin(c, p, g, x, y, T, B, in, out, seed, step, loss, (cudaStream_t)stream);
+    ZRB_TRY(zrb_train_step_grads(c, p, g, x, y, T, B, in, out, seed, step, loss, stream));   // validation engine: all at once
+    c->bwd_next_layer = c->cfg.layers - 1;
+    return ZRB_OK;
+}
+
+int zrb_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int32_t layer, void* stream) {
+    ZRB_REQUIRE(c && p && g, "null argument");
+    ZRB_REQUIRE(layer >= 0 && layer < c->cfg.layers, "layer %d out of range", layer);
+    if (c->cfg.engine == ZRB_ENGINE_TC) return tc_train_step_layer(c, p, g, layer, (cudaStream_t)stream);
+    if (layer != c->bwd_next_layer) {
+        set_error("backward layers must be visited in order L-1..0");
+        return ZRB_E_STATE;
+    }
+    c->bwd_next_layer = layer - 1;
+    return ZRB_OK;
+}
+
 int zrb_train_step_update(zrb_ctx* c, const zrb_params* p, const zrb_params* g, float lr, float max_norm,
                           float* norm_out, void* stream) {
     ZRB_REQUIRE(c && p && g, "null argument");

@@ -40,6 +40,9 @@ struct zrb_ctx {
     bool explicit_masks_set = false;
     const uint8_t* explicit_masks[ZRB_MAX_LAYERS + 1] = {};
     int64_t weights_version = 1;           // bumped whenever parameter values change
+    float* bwd_dy = nullptr;               // phased backward: grad wrt the next layer's output / scratch
+    float* bwd_dx = nullptr;
+    int bwd_next_layer = -1;
 
     zrb_tc_state* tc = nullptr;
 
@@ -73,6 +76,10 @@ int tc_backward(zrb_ctx* c, const zrb_params* p, const float* dscores, const zrb
 int tc_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, const int64_t* x, const int64_t* y,
                         int T, int B, const zrb_states* in, const zrb_states* out, uint64_t seed, uint64_t step,
                         float* loss, cudaStream_t s);
+int tc_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, const int64_t* x, const int64_t* y,
+                        int T, int B, const zrb_states* in, const zrb_states* out, uint64_t seed, uint64_t step,
+                        float* loss, cudaStream_t s);
+int tc_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int l, cudaStream_t s);
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries);
 int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
               cudaStream_t s);

@@ -178,14 +178,16 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
 }
 
 // backward from the scaled fp16 image dS_h already in place
-static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_params* g, cudaStream_t s) {
+// projection backward: afterwards fc.W / fc.b gradients are complete and c->bwd_dy holds d loss / d act[L]
+static int tc_backward_head(zrb_ctx* c, const zrb_params* p, const zrb_params* g, cudaStream_t s) {
     zrb_tc_state* t = c->tc;
-    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab, T = c->T, B = c->B, N = T * B;
-    const int Hp = t->Hp, G4p = t->G4p, Vp = t->Vp;
-    const size_t bh = (size_t)B * H;
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab, N = c->T * c->B;
+    const int Hp = t->Hp, Vp = t->Vp;
     const float inv = 1.f / kGradScale;
     float* dY = c->dy;
-    float* dX = c->dx;
+    c->bwd_dy = c->dy;
+    c->bwd_dx = c->dx;
+    c->bwd_next_layer = L - 1;
     {
         ProfScope ps(c, ZRB_PROF_PROJ_BWD, s);
         // dA[N,H] = dS[N,V] * W[V,H]       (W image read MN-major)
@@ -194,7 +196,24 @@ static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_par
         ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s));
         ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, nullptr, N, V, inv, s));
     }
-    for (int l = L - 1; l >= 0; --l) {
+    return ZRB_OK;
+}
+
+// backward of layer l (must be called for l = L-1, ..., 0 in that order): afterwards the layer's four
+// gradients are complete; l == 0 also finishes the embedding gradient
+static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int l, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, V = c->cfg.vocab, T = c->T, B = c->B, N = T * B;
+    const int Hp = t->Hp, G4p = t->G4p;
+    const size_t bh = (size_t)B * H;
+    const float inv = 1.f / kGradScale;
+    if (l != c->bwd_next_layer) {
+        set_error("backward layers must be visited in order L-1..0 (expected %d, got %d)", c->bwd_next_layer, l);
+        return ZRB_E_STATE;
+    }
+    float* dY = c->bwd_dy;
+    float* dX = c->bwd_dx;
+    {
         MaskSrc m = site_mask(c, l + 1);
         ZRB_CUDA(cudaMemsetAsync(c->dc, 0, bh * sizeof(float), s));
         if (t->bplan.ok) {
@@ -225,9 +244,19 @@ static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_par
         else ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
         float* tmp = dY; dY = dX; dX = tmp;
     }
+    c->bwd_dy = dY;
+    c->bwd_dx = dX;
+    c->bwd_next_layer = l - 1;
+    if (l > 0) return ZRB_OK;
     ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);
     ZRB_CUDA(cudaMemsetAsync(g->embed_w, 0, (size_t)V * H * sizeof(float), s));
     ZRB_TRY(embed_dropout_bwd(dY, c->x_saved, g->embed_w, N, H, V, site_mask(c, 0), s));
+    return ZRB_OK;
+}
+
+static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_params* g, cudaStream_t s) {
+    ZRB_TRY(tc_backward_head(c, p, g, s));
+    for (int l = c->cfg.layers - 1; l >= 0; --l) ZRB_TRY(tc_backward_layer(c, p, g, l, s));
     return ZRB_OK;
 }
 
@@ -251,6 +280,25 @@ int tc_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
                             c->tc->Vp, kGradScale));
     }
     return tc_backward_from_image(c, p, g, s);
+}
+
+int tc_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, const int64_t* x, const int64_t* y,
+                        int T, int B, const zrb_states* in, const zrb_states* out, uint64_t seed, uint64_t step,
+                        float* loss, cudaStream_t s) {
+    c->T = T; c->B = B; c->train = 1; c->seed = seed; c->step = step;
+    c->have_fwd = false;
+    ZRB_TRY(tc_forward(c, p, x, in, out, c->scores, s));
+    c->have_fwd = true;
+    {
+        ProfScope ps(c, ZRB_PROF_SOFTMAX, s);
+        ZRB_TRY(softmax_nll(c->scores, y, T * B, c->cfg.vocab, B, c->row_loss, loss, nullptr, nullptr, s, c->tc->dS_h,
+                            c->tc->Vp, kGradScale));
+    }
+    return tc_backward_head(c, p, g, s);
+}
+
+int tc_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int l, cudaStream_t s) {
+    return tc_backward_layer(c, p, g, l, s);
 }
 
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries) {

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -71,6 +72,19 @@ class Trainer:
         self._hloss = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.step = 0
         self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        # data-parallel buckets of the flat gradient buffer, in the order backward completes them:
+        # [fc.W, fc.b], layer L-1, ..., layer 1, [embed.W + layer 0]
+        L = model.layer_num
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        self._buckets = [(offs[1 + 4 * L], offs[-1])]
+        for l in range(L - 1, 0, -1):
+            self._buckets.append((offs[1 + 4 * l], offs[1 + 4 * (l + 1)]))
+        self._buckets.append((0, offs[1 + 4]))
+        self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # reduce buckets under the rest of backward (1) or all-reduce once after backward (0)
+        self.overlap = os.environ.get("ZRB_DP_OVERLAP", "0") == "1"
         self.ctx = model._context(seq_length, batch_size)
         _lib.check(_lib.load().zrb_params_changed(self.ctx))
 
@@ -87,15 +101,48 @@ class Trainer:
         tensors (no host sync)."""
         lib = _lib.load()
         T, B = x.shape
-        _lib.check(lib.zrb_train_step_grads(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x), _lib.ptr(y),
-                                            T, B, C.byref(self._st), C.byref(self._st), self.seed, self.step,
-                                            _lib.ptr(self.loss), self._stream()))
-        if self.world > 1:
-            allreduce_sum_(self.flat_g, self.pg)
+        if self.world > 1 and self.overlap:
+            self._grads_overlapped(lib, x, y, T, B)
+        else:
+            _lib.check(lib.zrb_train_step_grads(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x),
+                                                _lib.ptr(y), T, B, C.byref(self._st), C.byref(self._st), self.seed,
+                                                self.step, _lib.ptr(self.loss), self._stream()))
+            if self.world > 1:
+                allreduce_sum_(self.flat_g, self.pg)
         _lib.check(lib.zrb_train_step_update(self.ctx, C.byref(self._ps), C.byref(self._gs), float(lr),
                                              float(max_norm), _lib.ptr(self.norm), self._stream()))
         self.step += 1
         return self.loss, self.norm
+
+    def _grads_overlapped(self, lib, x, y, T, B):
+        """Backward in phases (zrb_train_step_begin / _layer); as soon as a bucket of the flat gradient
+        buffer is complete its SUM all-reduce is enqueued on a side stream, so the reduction of
+        fc / upper-layer gradients runs under the rest of backward.  Still one logical all-reduce
+        of the gradient buffer per step (ordered NCCL calls over disjoint slices)."""
+        cur = torch.cuda.current_stream(self.dev)
+        comm = self._comm_stream
+        L = self.model.layer_num
+
+        def reduce_bucket(k):
+            lo, hi = self._buckets[k]
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                allreduce_sum_(self.flat_g[lo:hi], self.pg)
+
+        _lib.check(lib.zrb_train_step_begin(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x), _lib.ptr(y),
+                                            T, B, C.byref(self._st), C.byref(self._st), self.seed, self.step,
+                                            _lib.ptr(self.loss), cur.cuda_stream))
+        reduce_bucket(0)
+        k = 1
+        for l in range(L - 1, -1, -1):
+            _lib.check(lib.zrb_train_step_layer(self.ctx, C.byref(self._ps), C.byref(self._gs), l, cur.cuda_stream))
+            if l >= 1:
+                reduce_bucket(k)
+                k += 1
+        reduce_bucket(len(self._buckets) - 1)
+        cur.wait_stream(comm)
 
     def train_step_host(self, x, y, lr, max_norm):
         """x, y: [T,B] int64 CPU tensors exactly as main.py:71-72 builds them.  Copies them to
