@@ -285,7 +285,9 @@ def test_large_config_against_fp64_oracle(engine):
     assert torch.equal(scores, scores_a)
     params = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in m.named_parameters()}
     sc, st, cache = O.model_fwd(params, x.numpy(), O.zero_states(L, B, H, np.float64), L)
-    tol = TOL[engine]
+    # measured at this config (tools/measure_error.py): tc 3.4e-4 logits / <= 5.7e-4 grads of each tensor's
+    # scale; the reference's own cuDNN-TF32 path 1.7e-4 / <= 4.7e-4.  Held to ~3x the measurement here.
+    tol = dict(TOL[engine], fwd=1.2e-3, grad=2e-3) if engine == "tc" else TOL[engine]
     _scale_close(scores.detach().cpu().numpy(), sc, tol["fwd"], "L logits")
     for l in range(L):
         _scale_close(states[l][0].reshape(B, H).cpu().numpy(), st[l][0], tol["fwd"], f"L h{l}")

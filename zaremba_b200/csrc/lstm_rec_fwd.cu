@@ -155,19 +155,29 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             if (tr && tid == 0) a.trace[t * 8 + 3] = clock64();
             // drain: warp (quad, half) sums accumulators 2*half, 2*half+1 of TMEM lanes [32*quad, +32)
             // into staging buffer `half`; accumulator row i sits in lane (i % 16) + 32 * (i / 16)
-            {   // warp (quad, half): TMEM lanes [32*quad, +32), accumulators half and half+2 summed -> staging buffer `half`
-                const bool u0 = half < ksteps, u1 = half + 2 < ksteps;   // an issuer with no K step leaves its accumulator unwritten
+            {   // warp (quad, half): TMEM lanes [32*quad, +32); accumulators half, half+2, ... are summed
                 for (int c0 = 0; c0 < Bp; c0 += 8) {
-                    uint32_t v0[8], v1[8];
+                    // issue every accumulator's load, wait once, then sum (an issuer with no K step leaves its
+                    // accumulator unwritten: skipped by a warp-uniform test)
+                    uint32_t v[kRecMmaWarps / 2][8];
                     const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
-                    tmem_ld_32x8(base + half * 32, v0);
-                    tmem_ld_32x8(base + (half + 2) * 32, v1);
+#pragma unroll
+                    for (int ai = 0; ai < kRecMmaWarps / 2; ++ai)
+                        if (half + 2 * ai < ksteps) tmem_ld_32x8(base + (half + 2 * ai) * 32, v[ai]);
                     tmem_ld_wait();
+                    float acc[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+                    for (int ai = 0; ai < kRecMmaWarps / 2; ++ai)
+                        if (half + 2 * ai < ksteps) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(v[ai][i]);
+                        }
                     if (lane < 16) {
                         float* dst = sD + (half * 64 + 16 * quad + lane) * ldd + c0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            dst[i] = (u0 ? __uint_as_float(v0[i]) : 0.f) + (u1 ? __uint_as_float(v1[i]) : 0.f);
+                        for (int i = 0; i < 8; ++i) dst[i] = acc[i];
                     }
                 }
             }

@@ -9,13 +9,15 @@ using namespace tc;
 constexpr int kRecEpiWarps = 8;                       // warps 0-7: accumulator drain + cell math
 constexpr int kRecEpiThreads = kRecEpiWarps * 32;
 constexpr int kRecMmaWarp = 8;                        // warps 8..11: lane 0 of warp 8+i issues K steps i, i+4, ... into its
-constexpr int kRecMmaWarps = 4;                       //   OWN accumulator i (warp 8 also owns the TMEM allocation)
-constexpr int kRecLoadWarp = 12;                      // lane 0: grid-barrier wait + bulk copies
-constexpr int kRecThreads = 416;
-constexpr int kRecTmemCols = 128;                     // four fp32 accumulators, N <= 32 columns each.  tcgen05.mma has a
+constexpr int kRecMmaWarps = 4;                       //   OWN accumulator i (warp 8 also owns the TMEM allocation).  8 issuers
+                                                      //   cut the MMA phase to ~2100 clk but the accumulator drain is bound by the
+                                                      //   64 B/clk TMEM read port, so 4 and 8 end up equal (measured)
+constexpr int kRecLoadWarp = kRecMmaWarp + kRecMmaWarps;   // lane 0: grid-barrier wait + bulk copies
+constexpr int kRecThreads = (kRecLoadWarp + 1) * 32;
+constexpr int kRecTmemCols = 32 * kRecMmaWarps;       // one fp32 accumulator (N <= 32 columns) per issuer.  tcgen05.mma has a
                                                       // ~45 clk floor per instruction for N <= 64 (measured); one issuing
                                                       // thread only reaches ~90 clk (descriptor math + R2UR in series with
-                                                      // the issue); 2 threads with private accumulators reach ~57, 4 threads the floor
+                                                      // the issue); 2 threads with private accumulators reach ~57, 4 threads ~33 clk per MMA
 constexpr int kRecPieces = 4;                         // operand image arrives in this many bulk copies
 constexpr int kRecMaxCell = 2;                        // (unit, batch) cells per epilogue thread
 constexpr long long kSpinCycles = 6000000000ll;  // ~3 s at 2 GHz: a lost wake-up traps instead of hanging the GPU
