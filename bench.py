@@ -231,8 +231,15 @@ def run_ours(args, c, name):
             ach, peak, unit, bound = amount / (ms_step * 1e-3) / 1e12, peaks["tensor"], "TFLOP/s", "tensor"
         else:
             ach, peak, unit, bound = amount / (ms_step * 1e-3) / 1e9, peaks["hbm"], "GB/s", "hbm"
+        traffic = None
+        try:
+            ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+            if ent and name == "large":
+                traffic = ent["bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": bound, "kernel_class": top, "achieved": ach, "peak": peak, "unit": unit,
-                    "frac": ach / peak, "traffic": None, "peak_source": peaks["src"],
+                    "frac": ach / peak, "traffic": traffic, "peak_source": peaks["src"],
                     "ms_per_step_in_class": ms_step, "launch_groups_per_step": per_class[top][1],
                     "class_ms_per_step": {n: round(v[0], 4) for n, v in per_class.items()},
                     "whole_step_tflops": flops_per_token(c) * T * B / (dev_ms / K * 1e-3) / 1e12}
