@@ -127,7 +127,10 @@ def run_reference(args, c, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = cpu_port_leg(c, 0, steps=args.steps, warmup=max(1, args.warmup))
+    # bounded sample: at most ~100 s of CPU work whatever --steps says (0.73 s/step for Large on 64 threads)
+    probe, dt1 = cpu_port_leg(c, 0, steps=1, warmup=1)
+    run_steps = max(3, min(args.steps, int(100.0 / max(dt1, 1e-3))))
+    base, dt = cpu_port_leg(c, 0, steps=run_steps, warmup=min(max(1, args.warmup), 3))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -267,8 +270,8 @@ def run_ours(args, c, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--config", default="large", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default=os.environ.get("ZRB_ENGINE", "tc"), choices=["tc", "simt"])
