@@ -149,8 +149,37 @@ int  zrb_train_step_begin(zrb_ctx* ctx, const zrb_params* p, const zrb_params* g
                           uint64_t seed, uint64_t step, float* loss, void* stream);
 int  zrb_train_step_layer(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads, int32_t layer,
                           void* stream);
+/* Sparse form of the embedding gradient for data parallelism.  The gradient of embed.W (model.py:14) is
+ * non-zero only in the rows of this window's tokens.  With a rows buffer set, backward writes the N = T*B
+ * dropout-masked gradient rows [N,H] there INSTEAD of scattering them into the dense table gradient; ranks
+ * all-gather ids and rows (4 MB each instead of a 60 MB all-reduce) and zrb_embed_scatter_rows builds the
+ * dense gradient: rows with equal id are summed in index order by the first occurrence, without atomics, so
+ * all ranks get identical bits.  Pass NULL to return to the dense scatter. */
+int  zrb_set_embed_rows_out(zrb_ctx* ctx, float* rows);
+int  zrb_embed_scatter_rows(zrb_ctx* ctx, float* grad_embed, const int64_t* ids, const float* rows,
+                            int64_t n_rows, void* stream);
 int  zrb_train_step_update(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,
                            float lr, float max_norm, float* norm_out, void* stream);
+
+/* ---- data-parallel gradient all-reduce over NVLink peer memory, copy engines only (dp_ce.cu) ----------
+ * One process per GPU.  zrb_dp_create allocates the flat gradient buffer (use zrb_dp_grad_buffer as the
+ * `grads` storage) and a flag block and exports them through CUDA IPC: exchange the 128-byte blobs of all
+ * ranks on the host (rank order) and hand them to zrb_dp_import.  Per step: zrb_dp_begin_step before the
+ * first gradient write; after each bucket of the flat buffer is complete on `stream`
+ * (zrb_train_step_begin / _layer) call zrb_dp_allreduce_bucket -- same bucket sequence on every rank, SUM
+ * semantics, the last bucket with last = 1 makes `stream` wait for the whole reduction.  No SM is used for
+ * the transport (cuStreamWaitValue32 / cuStreamWriteValue32 flags + peer cudaMemcpyAsync), so it overlaps
+ * with the persistent recurrence kernels, which NCCL's channels do not. */
+typedef struct zrb_dp zrb_dp;
+int    zrb_dp_create(int32_t rank, int32_t world, int64_t n_grad, zrb_dp** out);
+void   zrb_dp_destroy(zrb_dp* dp);
+float* zrb_dp_grad_buffer(zrb_dp* dp);
+int    zrb_dp_export(zrb_dp* dp, void* h_blob128);
+int    zrb_dp_import(zrb_dp* dp, const void* h_blobs);
+int    zrb_dp_begin_step(zrb_dp* dp, void* stream);
+int    zrb_dp_allreduce_bucket(zrb_dp* dp, int32_t bucket, int64_t lo, int64_t hi, int32_t last, void* stream);
+/* join: `stream` waits for all bucket reductions enqueued in this step (alternative to last = 1) */
+int    zrb_dp_finish_step(zrb_dp* dp, void* stream);
 
 /* perplexity's inner step (main.py:91-94) without materialising scores for the caller:
  * forward in eval mode + loss (+ per-token target probabilities for the ensemble). */

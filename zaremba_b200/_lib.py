@@ -62,6 +62,8 @@ _SIGNATURES = {
                                        C.c_int32, C.POINTER(ZrbStates), C.POINTER(ZrbStates), C.c_uint64,
                                        C.c_uint64, _vp, _vp]),
     "zrb_train_step_layer": (C.c_int, [_vp, C.POINTER(ZrbParams), C.POINTER(ZrbParams), C.c_int32, _vp]),
+    "zrb_set_embed_rows_out": (C.c_int, [_vp, _vp]),
+    "zrb_embed_scatter_rows": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp]),
     "zrb_train_step_update": (C.c_int, [_vp, C.POINTER(ZrbParams), C.POINTER(ZrbParams), C.c_float, C.c_float,
                                         _vp, _vp]),
     "zrb_eval_step": (C.c_int, [_vp, C.POINTER(ZrbParams), _vp, _vp, C.c_int32, C.c_int32, C.POINTER(ZrbStates),
@@ -69,6 +71,14 @@ _SIGNATURES = {
     "zrb_train_step_host": (C.c_int, [_vp, C.POINTER(ZrbParams), C.POINTER(ZrbParams), _vp, _vp, C.c_int32,
                                       C.c_int32, C.POINTER(ZrbStates), C.POINTER(ZrbStates), C.c_uint64,
                                       C.c_uint64, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "zrb_dp_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(_vp)]),
+    "zrb_dp_destroy": (None, [_vp]),
+    "zrb_dp_grad_buffer": (_vp, [_vp]),
+    "zrb_dp_export": (C.c_int, [_vp, _vp]),
+    "zrb_dp_import": (C.c_int, [_vp, _vp]),
+    "zrb_dp_begin_step": (C.c_int, [_vp, _vp]),
+    "zrb_dp_finish_step": (C.c_int, [_vp, _vp]),
+    "zrb_dp_allreduce_bucket": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _vp]),
     "zrb_prof_enable": (C.c_int, [_vp, C.c_int32]),
     "zrb_prof_read": (C.c_int, [_vp, _vp, _vp]),
     "zrb_prof_rec_trace": (C.c_int, [_vp, _vp, C.c_int32]),

@@ -265,6 +265,21 @@ int zrb_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, i
     return ZRB_OK;
 }
 
+int zrb_set_embed_rows_out(zrb_ctx* c, float* rows) {
+    ZRB_REQUIRE(c, "null ctx");
+    c->embed_rows_out = rows;
+    return ZRB_OK;
+}
+
+int zrb_embed_scatter_rows(zrb_ctx* c, float* grad_embed, const int64_t* ids, const float* rows, int64_t n_rows,
+                           void* stream) {
+    ZRB_REQUIRE(c && grad_embed && ids && rows && n_rows >= 0, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);
+    ZRB_CUDA(cudaMemsetAsync(grad_embed, 0, (size_t)c->cfg.vocab * c->cfg.hidden * sizeof(float), s));
+    return embed_scatter_rows(ids, rows, grad_embed, (int)n_rows, c->cfg.hidden, c->cfg.vocab, s);
+}
+
 int zrb_train_step_update(zrb_ctx* c, const zrb_params* p, const zrb_params* g, float lr, float max_norm,
                           float* norm_out, void* stream) {
     ZRB_REQUIRE(c && p && g, "null argument");

@@ -43,6 +43,8 @@ struct zrb_ctx {
     float* bwd_dy = nullptr;               // phased backward: grad wrt the next layer's output / scratch
     float* bwd_dx = nullptr;
     int bwd_next_layer = -1;
+    float* embed_rows_out = nullptr;       // if set: backward emits the embedding gradient as N masked rows here
+                                           // instead of scattering into the dense table gradient (data parallel)
 
     zrb_tc_state* tc = nullptr;
 

@@ -88,6 +88,7 @@ int simt_backward(zrb_ctx* c, const zrb_params* p, const float* dscores, const z
         float* tmp = dY; dY = dX; dX = tmp;
     }
     ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);
+    if (c->embed_rows_out) return embed_rows(dY, c->embed_rows_out, N, H, site_mask(c, 0), s);
     ZRB_CUDA(cudaMemsetAsync(g->embed_w, 0, (size_t)V * H * sizeof(float), s));
     ZRB_TRY(embed_dropout_bwd(dY, c->x_saved, g->embed_w, N, H, V, site_mask(c, 0), s));
     return ZRB_OK;

@@ -290,6 +290,64 @@ int softmax_nll(const float* scores, const int64_t* y, int N, int V, int B, floa
     return ZRB_OK;
 }
 
+// ---- sparse form of the embedding gradient (data parallel) ------------------------------------------------
+// rows[n, :] = dropout-masked dA[n, :]: what embed_dropout_bwd would scatter, kept as N rows so that ranks can
+// exchange 4 MB of rows instead of all-reducing the dense 60 MB table gradient.
+__global__ void embed_rows_kernel(const float* __restrict__ dA, float* __restrict__ rows, int N, int H, MaskSrc m) {
+    int n = blockIdx.x;
+    uint64_t n_total = (uint64_t)N * H;
+    for (int j = threadIdx.x; j < H; j += blockDim.x)
+        rows[(int64_t)n * H + j] = dA[(int64_t)n * H + j] * mask_mul1(m, (uint64_t)n * H + j, n_total);
+}
+int embed_rows(const float* dA, float* rows, int N, int H, MaskSrc m, cudaStream_t s) {
+    if (!N) return ZRB_OK;
+    embed_rows_kernel<<<N, 256, 0, s>>>(dA, rows, N, H, m);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
+// dW[id, :] = sum of rows[n', :] over all n' with ids[n'] == id, added in ascending n' by the block of the FIRST
+// occurrence: no atomics, so every rank that holds the same (ids, rows) arrays gets bit-identical sums.
+// dW must be zero where no token points.
+__global__ void embed_scatter_rows_kernel(const int64_t* __restrict__ ids, const float* __restrict__ rows,
+                                          float* __restrict__ dW, int n_rows, int H, int V) {
+    __shared__ int s_first;
+    __shared__ uint32_t s_match[256];          // bitmap of k in [n, n + 8192) with ids[k] == id
+    const int n = blockIdx.x;
+    const int64_t id = ids[n];
+    if (id < 0 || id >= V) return;
+    if (threadIdx.x == 0) s_first = 1;
+    for (int w = threadIdx.x; w < 256; w += blockDim.x) s_match[w] = 0u;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x)
+        if (ids[k] == id) s_first = 0;
+    __syncthreads();
+    if (!s_first) return;
+    for (int k = n + threadIdx.x; k < n_rows; k += blockDim.x)
+        if (ids[k] == id) atomicOr(&s_match[(k - n) >> 5], 1u << ((k - n) & 31));
+    __syncthreads();
+    const int words = (n_rows - n + 31) >> 5;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float acc = 0.f;
+        for (int w = 0; w < words; ++w) {      // ascending k: the order of the additions is fixed
+            uint32_t bits = s_match[w];
+            while (bits) {
+                const int k = n + (w << 5) + (__ffs(bits) - 1);
+                acc += rows[(int64_t)k * H + j];
+                bits &= bits - 1;
+            }
+        }
+        dW[id * (int64_t)H + j] = acc;
+    }
+}
+int embed_scatter_rows(const int64_t* ids, const float* rows, float* dW, int n_rows, int H, int V, cudaStream_t s) {
+    if (!n_rows) return ZRB_OK;
+    ZRB_REQUIRE(n_rows <= 8192, "embed_scatter_rows handles at most 8192 rows per step (got %d)", n_rows);
+    embed_scatter_rows_kernel<<<n_rows, 256, 0, s>>>(ids, rows, dW, n_rows, H, V);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
 __global__ void dropout_mask_kernel(MaskSrc m, int64_t n, uint8_t* __restrict__ out) {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (4 * g >= n) return;

@@ -51,7 +51,14 @@ class Trainer:
         sizes = [p.numel() for p in params]
         # one flat parameter buffer and one flat gradient buffer; the nn.Parameters become views
         self.flat_p = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        # DP transport: "ce" = copy engines over NVLink peer memory (dp_ce.cu, overlaps with backward),
+        # "nccl" = one torch.distributed all_reduce after backward
+        self.transport = os.environ.get("ZRB_DP_TRANSPORT", "ce") if self.world > 1 else None
+        self._dp = None
+        if self.transport == "ce":
+            self.flat_g = self._create_ce_transport(sum(sizes))
+        else:
+            self.flat_g = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
         off = 0
         with torch.no_grad():
             for p, n in zip(params, sizes):
@@ -82,11 +89,74 @@ class Trainer:
         for l in range(L - 1, 0, -1):
             self._buckets.append((offs[1 + 4 * l], offs[1 + 4 * (l + 1)]))
         self._buckets.append((0, offs[1 + 4]))
+        self._embed_end = offs[1]
         self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         # reduce buckets under the rest of backward (1) or all-reduce once after backward (0)
         self.overlap = os.environ.get("ZRB_DP_OVERLAP", "0") == "1"
         self.ctx = model._context(seq_length, batch_size)
         _lib.check(_lib.load().zrb_params_changed(self.ctx))
+        if self.transport == "ce":
+            H, N = model.hidden_size, batch_size * seq_length
+            self._rows = torch.zeros(N, H, device=dev)
+            self._rows_all = torch.zeros(self.world * N, H, device=dev)
+            self._ids_all = torch.zeros(self.world * N, dtype=torch.int64, device=dev)
+            # (the rows buffer is handed to the context only for the duration of a DP step, see _grads_ce)
+
+    def _create_ce_transport(self, n):
+        """zrb_dp_create + CUDA-IPC handle exchange; returns the library-owned flat gradient buffer as a tensor."""
+        lib = _lib.load()
+        rank = dist.get_rank(self.pg)
+        dp = C.c_void_p()
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.zrb_dp_create(rank, self.world, n, C.byref(dp)))
+            blob = (C.c_uint8 * 128)()
+            _lib.check(lib.zrb_dp_export(dp, blob))
+            mine = torch.tensor(list(blob), dtype=torch.uint8, device=self.dev)
+            allb = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allb, mine, group=self.pg)
+            host = torch.stack(allb).cpu().contiguous()
+            _lib.check(lib.zrb_dp_import(dp, C.c_void_p(host.data_ptr())))
+        self._dp = dp
+        ptr = lib.zrb_dp_grad_buffer(dp)
+
+        class _Ext:       # external CUDA memory -> torch tensor (no ownership), via the CUDA array interface
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+        self._ext = _Ext()
+        return torch.as_tensor(self._ext, device=self.dev)
+
+    def _grads_ce(self, lib, x, y, T, B):
+        """Backward in phases.  Buckets that finish early (fc, upper layers) are reduced over NVLink by the copy
+        engines underneath the rest of backward (zrb_dp_allreduce_bucket: no SM used, so the persistent
+        kernels keep the whole chip); the bucket that only completes with the end of backward
+        (embed + layer 0) cannot overlap with anything and goes through one NCCL all-reduce."""
+        st = self._stream()
+        L = self.model.layer_num
+        _lib.check(lib.zrb_set_embed_rows_out(self.ctx, _lib.ptr(self._rows)))
+        _lib.check(lib.zrb_dp_begin_step(self._dp, st))
+        _lib.check(lib.zrb_train_step_begin(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x), _lib.ptr(y),
+                                            T, B, C.byref(self._st), C.byref(self._st), self.seed, self.step,
+                                            _lib.ptr(self.loss), st))
+        nb = len(self._buckets)
+        lo, hi = self._buckets[0]
+        _lib.check(lib.zrb_dp_allreduce_bucket(self._dp, 0, lo, hi, 0, st))
+        k = 1
+        for l in range(L - 1, -1, -1):
+            _lib.check(lib.zrb_train_step_layer(self.ctx, C.byref(self._ps), C.byref(self._gs), l, st))
+            if l >= 1:
+                lo, hi = self._buckets[k]
+                _lib.check(lib.zrb_dp_allreduce_bucket(self._dp, k, lo, hi, 0, st))
+                k += 1
+        lo, hi = self._buckets[nb - 1]
+        # tail: layer-0 gradients through one NCCL all-reduce (alone on the GPU); the embedding gradient as rows
+        allreduce_sum_(self.flat_g[self._embed_end:hi], self.pg)
+        N = T * B
+        dist.all_gather_into_tensor(self._rows_all[: self.world * N], self._rows[:N], group=self.pg)
+        dist.all_gather_into_tensor(self._ids_all[: self.world * N], x.reshape(-1), group=self.pg)
+        _lib.check(lib.zrb_embed_scatter_rows(self.ctx, _lib.ptr(self.flat_g), _lib.ptr(self._ids_all),
+                                              _lib.ptr(self._rows_all), self.world * N, st))
+        _lib.check(lib.zrb_dp_finish_step(self._dp, st))
+        _lib.check(lib.zrb_set_embed_rows_out(self.ctx, None))
 
     def reset_states(self):
         for h, c in self.states:
@@ -101,7 +171,9 @@ class Trainer:
         tensors (no host sync)."""
         lib = _lib.load()
         T, B = x.shape
-        if self.world > 1 and self.overlap:
+        if self.world > 1 and self.transport == "ce":
+            self._grads_ce(lib, x, y, T, B)
+        elif self.world > 1 and self.overlap:
             self._grads_overlapped(lib, x, y, T, B)
         else:
             _lib.check(lib.zrb_train_step_grads(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x),
