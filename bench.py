@@ -250,7 +250,7 @@ def run_ours(args, c, name):
         "metric": METRIC, "value": tokens / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands, f32 accumulate/state" if args.engine == "tc" else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(name, c), "engine": args.engine, "parallelism": f"dp{world}", "dp_overlap": bool(getattr(tr, "overlap", False)) if world > 1 else None,
+        "config": {"workload": workload_name(name, c), "engine": args.engine, "parallelism": f"dp{world}", "dp_transport": getattr(tr, "transport", None),
                    "global_batch": B * world, "seq_len": T,
                    "l2": "no flush: per-step working set (fp32 params+grads 528 MB + activations) exceeds the 126 MB L2"
                    if name == "large" else "no flush; working set may fit L2 for this config"},

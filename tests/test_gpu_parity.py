@@ -383,3 +383,27 @@ def test_phased_backward_equals_monolithic(engine):
         assert hi == tr.flat_g.numel() and tr._buckets[-1][0] == 0
         assert sum(b - a for a, b in tr._buckets) == tr.flat_g.numel()
     assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-7 * float(grads[0].abs().max()) + 1e-9)
+
+
+def test_sparse_embedding_gradient_rows_and_scatter():
+    """Data-parallel form of the embedding gradient: zrb_set_embed_rows_out + zrb_embed_scatter_rows == the dense
+    scatter (np.add.at), with duplicate tokens, and bit-identical across repeated runs (integer accumulation)."""
+    import zaremba_b200
+    from zaremba_b200 import _lib
+    lib = _lib.load()
+    V, H, n = 211, 48, 700
+    m = zaremba_b200.Model(V, H, 1, 0.0, 0.1, engine="simt").to(_dev())
+    ctx = m._context(7, 5)
+    rng = np.random.default_rng(9)
+    ids = rng.integers(0, 40, size=n)          # few distinct ids: many duplicates
+    rows = (rng.normal(size=(n, H)) * 10.0 ** rng.integers(-6, 2, size=(n, 1))).astype(np.float32)
+    want = np.zeros((V, H), dtype=np.float64)
+    np.add.at(want, ids, rows.astype(np.float64))
+    idt, rt = torch.tensor(ids).cuda(), torch.tensor(rows).cuda()
+    outs = []
+    for rep in range(2):
+        g = torch.full((V, H), 7.0, device="cuda")
+        _lib.check(lib.zrb_embed_scatter_rows(ctx, _lib.ptr(g), _lib.ptr(idt), _lib.ptr(rt), n, None))
+        outs.append(g.clone())
+    assert torch.equal(outs[0], outs[1])
+    np.testing.assert_allclose(outs[0].cpu().numpy(), want, rtol=2e-6, atol=1e-9)

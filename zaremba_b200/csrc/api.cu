@@ -275,9 +275,14 @@ int zrb_embed_scatter_rows(zrb_ctx* c, float* grad_embed, const int64_t* ids, co
                            void* stream) {
     ZRB_REQUIRE(c && grad_embed && ids && rows && n_rows >= 0, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
+    if (n_rows > c->emb_cap_rows) {
+        if (!c->emb_first) ZRB_TRY(dalloc(c, &c->emb_first, (size_t)c->cfg.vocab));
+        ZRB_TRY(dalloc(c, &c->emb_acc, (size_t)n_rows * c->cfg.hidden));   // (a previous, smaller one is kept until destroy)
+        c->emb_cap_rows = n_rows;
+    }
     ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);
     ZRB_CUDA(cudaMemsetAsync(grad_embed, 0, (size_t)c->cfg.vocab * c->cfg.hidden * sizeof(float), s));
-    return embed_scatter_rows(ids, rows, grad_embed, (int)n_rows, c->cfg.hidden, c->cfg.vocab, s);
+    return embed_scatter_rows(ids, rows, grad_embed, (int)n_rows, c->cfg.hidden, c->cfg.vocab, c->emb_first, c->emb_acc, s);
 }
 
 int zrb_train_step_update(zrb_ctx* c, const zrb_params* p, const zrb_params* g, float lr, float max_norm,

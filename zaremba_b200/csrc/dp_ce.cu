@@ -8,8 +8,8 @@
 //
 // One process per GPU.  The flat gradient buffer and a small flag block are allocated here with cudaMalloc
 // and exported through CUDA IPC; every rank maps every peer.  Per bucket [lo,hi), split into `world` shards:
-//   ready      compute stream, after the bucket's gradients are complete: cuStreamWriteValue32 of a
-//              sequence number into every peer's flag block
+//   ready      compute stream, after the bucket's gradients are complete: ONE cuStreamWriteValue32 of a
+//              sequence number into the rank's own flag block (peers poll it through the IPC mapping)
 //   scatter    per peer p, on its own stream (copies from different peers run on different copy engines):
 //              cuStreamWaitValue32(ready[p]) ; cudaMemcpyAsync(staging[p] <- peer p's copy of MY shard)
 //   reduce     a small kernel sums the world-1 staged slices into my shard of g (fixed rank order:
@@ -31,7 +31,7 @@ struct zrb_dp {
     int rank = 0, world = 1;
     float* g = nullptr;            // flat gradient buffer (owned)
     int64_t n = 0;
-    uint32_t* flags = nullptr;     // [3][world][kMaxBuckets] ready / reduced / done, written by peers (owned)
+    uint32_t* flags = nullptr;     // [3][kMaxBuckets] ready / reduced / done: written locally, polled by peers (owned)
     float* staging = nullptr;      // [world-1][max_shard]
     int64_t max_shard = 0;
     std::vector<float*> peer_g;    // mapped peer gradient buffers (peer_g[rank] = g)
@@ -101,9 +101,10 @@ __global__ void dp_reduce_kernel(float* __restrict__ dst, const float* __restric
     }
 }
 
-static uint32_t* flag_ptr(uint32_t* base, int world, int kind, int src_rank, int bucket) {
-    return base + ((size_t)kind * world + src_rank) * kMaxBuckets + bucket;
-}
+// flag of `kind` (0 ready, 1 reduced, 2 done) for bucket b inside a rank's flag block.  Every rank writes only
+// its OWN block (one stream write per event instead of one per peer) and waits on the peers' blocks through the
+// IPC mapping.
+static uint32_t* flag_ptr(uint32_t* base, int kind, int bucket) { return base + (size_t)kind * kMaxBuckets + bucket; }
 
 }  // namespace zrb
 
@@ -119,8 +120,8 @@ int zrb_dp_create(int32_t rank, int32_t world, int64_t n_grad, zrb_dp** out) {
     d->max_shard = ((n_grad + world - 1) / world + 3) & ~(int64_t)3;
     ZRB_CUDA(cudaMalloc(&d->g, (size_t)n_grad * sizeof(float)));
     ZRB_CUDA(cudaMemset(d->g, 0, (size_t)n_grad * sizeof(float)));
-    ZRB_CUDA(cudaMalloc(&d->flags, (size_t)3 * world * kMaxBuckets * sizeof(uint32_t)));
-    ZRB_CUDA(cudaMemset(d->flags, 0, (size_t)3 * world * kMaxBuckets * sizeof(uint32_t)));
+    ZRB_CUDA(cudaMalloc(&d->flags, (size_t)3 * kMaxBuckets * sizeof(uint32_t)));
+    ZRB_CUDA(cudaMemset(d->flags, 0, (size_t)3 * kMaxBuckets * sizeof(uint32_t)));
     if (world > 1) ZRB_CUDA(cudaMalloc(&d->staging, (size_t)(world - 1) * d->max_shard * sizeof(float)));
     d->peer_g.assign(world, nullptr);
     d->peer_flags.assign(world, nullptr);
@@ -197,11 +198,14 @@ int zrb_dp_import(zrb_dp* d, const void* h_blobs) {
 int zrb_dp_begin_step(zrb_dp* d, void* compute_stream) {
     ZRB_REQUIRE(d, "null argument");
     if (d->world == 1 || d->last_done_seq == 0) return ZRB_OK;
+    cudaStream_t rs = d->reduce_stream;
     for (int p = 0; p < d->world; ++p) {
         if (p == d->rank) continue;
-        ZRB_CU(g_wait32((CUstream)compute_stream, (CUdeviceptr)flag_ptr(d->flags, d->world, 2, p, 0), d->last_done_seq,
+        ZRB_CU(g_wait32((CUstream)rs, (CUdeviceptr)flag_ptr(d->peer_flags[p], 2, 0), d->last_done_seq,
                         CU_STREAM_WAIT_VALUE_GEQ));
     }
+    ZRB_CUDA(cudaEventRecord(d->ev_done, rs));
+    ZRB_CUDA(cudaStreamWaitEvent((cudaStream_t)compute_stream, d->ev_done, 0));
     return ZRB_OK;
 }
 
@@ -216,8 +220,7 @@ int zrb_dp_finish_step(zrb_dp* d, void* compute_stream) {
     for (int p = 0; p < W; ++p)
         if (p != R)
             for (int c = 0; c < d->spp; ++c) ZRB_CUDA(cudaStreamWaitEvent(rs, d->ev_copy[p * d->spp + c], 0));
-    for (int p = 0; p < W; ++p)
-        if (p != R) ZRB_CU(g_write32((CUstream)rs, (CUdeviceptr)flag_ptr(d->peer_flags[p], W, 2, R, 0), seq, 0));
+    ZRB_CU(g_write32((CUstream)rs, (CUdeviceptr)flag_ptr(d->flags, 2, 0), seq, 0));
     ZRB_CUDA(cudaEventRecord(d->ev_done, rs));
     ZRB_CUDA(cudaStreamWaitEvent(cs, d->ev_done, 0));
     d->last_done_seq = seq;
@@ -238,8 +241,7 @@ int zrb_dp_allreduce_bucket(zrb_dp* d, int32_t b, int64_t lo, int64_t hi, int32_
     auto s_hi = [&](int r) { return lo + (int64_t)(r + 1) * shard < hi ? lo + (int64_t)(r + 1) * shard : hi; };
 
     // ready: after the bucket's last kernel on the compute stream, tell every peer
-    for (int p = 0; p < W; ++p)
-        if (p != R) ZRB_CU(g_write32((CUstream)cs, (CUdeviceptr)flag_ptr(d->peer_flags[p], W, 0, R, b), seq, 0));
+    ZRB_CU(g_write32((CUstream)cs, (CUdeviceptr)flag_ptr(d->flags, 0, b), seq, 0));
     ZRB_CUDA(cudaEventRecord(d->ev_ready, cs));
 
     // scatter phase: pull my shard of every peer's bucket (one stream per peer -> independent copy engines)
@@ -252,7 +254,7 @@ int zrb_dp_allreduce_bucket(zrb_dp* d, int32_t b, int64_t lo, int64_t hi, int32_
             cudaStream_t st = d->streams[p * d->spp + c];
             // the staging slot is reused by every bucket: the previous bucket's reduce kernel must have read it
             ZRB_CUDA(cudaStreamWaitEvent(st, d->ev_reduced, 0));
-            ZRB_CU(g_wait32((CUstream)st, (CUdeviceptr)flag_ptr(d->flags, W, 0, p, b), seq, CU_STREAM_WAIT_VALUE_GEQ));
+            ZRB_CU(g_wait32((CUstream)st, (CUdeviceptr)flag_ptr(d->peer_flags[p], 0, b), seq, CU_STREAM_WAIT_VALUE_GEQ));
             const int64_t o = (int64_t)c * piece, cnt = o < my_n ? (my_n - o < piece ? my_n - o : piece) : 0;
             if (cnt > 0)
                 ZRB_CUDA(cudaMemcpyAsync(d->staging + (size_t)slot * d->max_shard + o, d->peer_g[p] + my_lo + o,
@@ -274,8 +276,7 @@ int zrb_dp_allreduce_bucket(zrb_dp* d, int32_t b, int64_t lo, int64_t hi, int32_
         dp_reduce_kernel<<<blocks, 256, 0, rs>>>(d->g + my_lo, d->staging, d->max_shard, W - 1, my_n);
         ZRB_KERNEL_CHECK();
     }
-    for (int p = 0; p < W; ++p)
-        if (p != R) ZRB_CU(g_write32((CUstream)rs, (CUdeviceptr)flag_ptr(d->peer_flags[p], W, 1, R, b), seq, 0));
+    ZRB_CU(g_write32((CUstream)rs, (CUdeviceptr)flag_ptr(d->flags, 1, b), seq, 0));
     ZRB_CUDA(cudaEventRecord(d->ev_reduced, rs));
 
     // gather phase: pull every peer's reduced shard into my g
@@ -285,7 +286,7 @@ int zrb_dp_allreduce_bucket(zrb_dp* d, int32_t b, int64_t lo, int64_t hi, int32_
         const int64_t piece = ((pn + d->spp - 1) / d->spp + 3) & ~(int64_t)3;
         for (int c = 0; c < d->spp; ++c) {
             cudaStream_t st = d->streams[p * d->spp + c];
-            ZRB_CU(g_wait32((CUstream)st, (CUdeviceptr)flag_ptr(d->flags, W, 1, p, b), seq, CU_STREAM_WAIT_VALUE_GEQ));
+            ZRB_CU(g_wait32((CUstream)st, (CUdeviceptr)flag_ptr(d->peer_flags[p], 1, b), seq, CU_STREAM_WAIT_VALUE_GEQ));
             const int64_t o = (int64_t)c * piece, cnt = o < pn ? (pn - o < piece ? pn - o : piece) : 0;
             if (cnt > 0)
                 ZRB_CUDA(cudaMemcpyAsync(d->g + pl + o, d->peer_g[p] + pl + o, (size_t)cnt * sizeof(float),
@@ -299,8 +300,7 @@ int zrb_dp_allreduce_bucket(zrb_dp* d, int32_t b, int64_t lo, int64_t hi, int32_
         for (int p = 0; p < W; ++p)
             if (p != R)
                 for (int c = 0; c < d->spp; ++c) ZRB_CUDA(cudaStreamWaitEvent(rs, d->ev_copy[p * d->spp + c], 0));
-        for (int p = 0; p < W; ++p)
-            if (p != R) ZRB_CU(g_write32((CUstream)rs, (CUdeviceptr)flag_ptr(d->peer_flags[p], W, 2, R, 0), seq, 0));
+        ZRB_CU(g_write32((CUstream)rs, (CUdeviceptr)flag_ptr(d->flags, 2, 0), seq, 0));
         ZRB_CUDA(cudaEventRecord(d->ev_done, rs));
         ZRB_CUDA(cudaStreamWaitEvent(cs, d->ev_done, 0));
         d->last_done_seq = seq;

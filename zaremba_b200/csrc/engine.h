@@ -43,6 +43,9 @@ struct zrb_ctx {
     float* bwd_dy = nullptr;               // phased backward: grad wrt the next layer's output / scratch
     float* bwd_dx = nullptr;
     int bwd_next_layer = -1;
+    int* emb_first = nullptr;              // workspace of zrb_embed_scatter_rows (allocated on first use)
+    long long* emb_acc = nullptr;
+    int64_t emb_cap_rows = 0;
     float* embed_rows_out = nullptr;       // if set: backward emits the embedding gradient as N masked rows here
                                            // instead of scattering into the dense table gradient (data parallel)
 

@@ -31,7 +31,8 @@ int softmax_nll(const float* scores, const int64_t* y, int N, int V, int B, floa
                 float* dscores, float* tgt_prob, cudaStream_t s, __half* ds_h = nullptr, int64_t ld_s = 0,
                 float h_scale = 1.f);
 int embed_rows(const float* dA, float* rows, int N, int H, MaskSrc m, cudaStream_t s);
-int embed_scatter_rows(const int64_t* ids, const float* rows, float* dW, int n_rows, int H, int V, cudaStream_t s);
+int embed_scatter_rows(const int64_t* ids, const float* rows, float* dW, int n_rows, int H, int V, int* first,
+                       long long* acc, cudaStream_t s);
 int dropout_mask_bytes(MaskSrc m, int64_t n, uint8_t* out, cudaStream_t s);
 
 // ---- optim.cu ----------------------------------------------------------------------------

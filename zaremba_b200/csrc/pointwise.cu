@@ -306,44 +306,45 @@ int embed_rows(const float* dA, float* rows, int N, int H, MaskSrc m, cudaStream
     return ZRB_OK;
 }
 
-// dW[id, :] = sum of rows[n', :] over all n' with ids[n'] == id, added in ascending n' by the block of the FIRST
-// occurrence: no atomics, so every rank that holds the same (ids, rows) arrays gets bit-identical sums.
-// dW must be zero where no token points.
-__global__ void embed_scatter_rows_kernel(const int64_t* __restrict__ ids, const float* __restrict__ rows,
-                                          float* __restrict__ dW, int n_rows, int H, int V) {
-    __shared__ int s_first;
-    __shared__ uint32_t s_match[256];          // bitmap of k in [n, n + 8192) with ids[k] == id
+// dW[id, :] = sum of rows[n, :] over all n with ids[n] == id, bit-identical on every rank that holds the same
+// (ids, rows) arrays: the rows are accumulated as 64-bit fixed point (2^-40 resolution, |x| < 8e6) with integer
+// atomics, whose result does not depend on the order of the additions, into the slot of the id's first
+// occurrence (atomicMin), then converted back to fp32 once.
+__global__ void embed_first_kernel(const int64_t* __restrict__ ids, int* __restrict__ first, int n_rows, int V) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_rows) return;
+    int64_t id = ids[n];
+    if (id >= 0 && id < V) atomicMin(first + id, n);
+}
+__global__ void embed_accum_kernel(const int64_t* __restrict__ ids, const float* __restrict__ rows,
+                                   const int* __restrict__ first, long long* __restrict__ acc, int n_rows, int H, int V) {
     const int n = blockIdx.x;
     const int64_t id = ids[n];
     if (id < 0 || id >= V) return;
-    if (threadIdx.x == 0) s_first = 1;
-    for (int w = threadIdx.x; w < 256; w += blockDim.x) s_match[w] = 0u;
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += blockDim.x)
-        if (ids[k] == id) s_first = 0;
-    __syncthreads();
-    if (!s_first) return;
-    for (int k = n + threadIdx.x; k < n_rows; k += blockDim.x)
-        if (ids[k] == id) atomicOr(&s_match[(k - n) >> 5], 1u << ((k - n) & 31));
-    __syncthreads();
-    const int words = (n_rows - n + 31) >> 5;
+    long long* dst = acc + (int64_t)first[id] * H;
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
-        float acc = 0.f;
-        for (int w = 0; w < words; ++w) {      // ascending k: the order of the additions is fixed
-            uint32_t bits = s_match[w];
-            while (bits) {
-                const int k = n + (w << 5) + (__ffs(bits) - 1);
-                acc += rows[(int64_t)k * H + j];
-                bits &= bits - 1;
-            }
-        }
-        dW[id * (int64_t)H + j] = acc;
+        float v = rows[(int64_t)n * H + j];
+        if (v != 0.f) atomicAdd((unsigned long long*)(dst + j), (unsigned long long)__float2ll_rn(v * 1099511627776.f));
     }
 }
-int embed_scatter_rows(const int64_t* ids, const float* rows, float* dW, int n_rows, int H, int V, cudaStream_t s) {
+__global__ void embed_finish_kernel(const int64_t* __restrict__ ids, const int* __restrict__ first,
+                                    const long long* __restrict__ acc, float* __restrict__ dW, int n_rows, int H, int V) {
+    const int n = blockIdx.x;
+    const int64_t id = ids[n];
+    if (id < 0 || id >= V || first[id] != n) return;
+    for (int j = threadIdx.x; j < H; j += blockDim.x)
+        dW[id * (int64_t)H + j] = (float)((double)acc[(int64_t)n * H + j] * (1.0 / 1099511627776.0));
+}
+int embed_scatter_rows(const int64_t* ids, const float* rows, float* dW, int n_rows, int H, int V, int* first,
+                       long long* acc, cudaStream_t s) {
     if (!n_rows) return ZRB_OK;
-    ZRB_REQUIRE(n_rows <= 8192, "embed_scatter_rows handles at most 8192 rows per step (got %d)", n_rows);
-    embed_scatter_rows_kernel<<<n_rows, 256, 0, s>>>(ids, rows, dW, n_rows, H, V);
+    ZRB_CUDA(cudaMemsetAsync(first, 0x7f, (size_t)V * sizeof(int), s));           // 0x7f7f7f7f > any row index
+    ZRB_CUDA(cudaMemsetAsync(acc, 0, (size_t)n_rows * H * sizeof(long long), s));
+    embed_first_kernel<<<cdiv(n_rows, 256), 256, 0, s>>>(ids, first, n_rows, V);
+    ZRB_KERNEL_CHECK();
+    embed_accum_kernel<<<n_rows, 256, 0, s>>>(ids, rows, first, acc, n_rows, H, V);
+    ZRB_KERNEL_CHECK();
+    embed_finish_kernel<<<n_rows, 256, 0, s>>>(ids, first, acc, dW, n_rows, H, V);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }

@@ -53,7 +53,10 @@ class Trainer:
         self.flat_p = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
         # DP transport: "ce" = copy engines over NVLink peer memory (dp_ce.cu, overlaps with backward),
         # "nccl" = one torch.distributed all_reduce after backward
-        self.transport = os.environ.get("ZRB_DP_TRANSPORT", "ce") if self.world > 1 else None
+        # measured on 8xB200 (profiles/r01_bench_dp*.json): ce wins at 2 and 4 ranks (1.97 vs 2.23 ms, 2.10 vs
+        # 2.39 ms), NCCL/NVLS alone wins at 8 (2.41 vs 2.55 ms: seven small peer copies per phase)
+        default = "ce" if self.world <= 4 else "nccl"
+        self.transport = os.environ.get("ZRB_DP_TRANSPORT", default) if self.world > 1 else None
         self._dp = None
         if self.transport == "ce":
             self.flat_g = self._create_ce_transport(sum(sizes))
