@@ -311,15 +311,15 @@ int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries) {
     return n;
 }
 
-// clip + SGD (main.py:114-117).  With 16-byte-aligned matrices (H % 4 == 0) the update pass also
-// writes the fp16 operand images of the new weights, so the next forward needs no pack pass.
+// clip + SGD (main.py:114-117).  The update pass also writes the fp16 operand images of the new weights,
+// so the next forward needs no pack pass.
 int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
               cudaStream_t s) {
     zrb_tc_state* t = c->tc;
     const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
-    bool fuse = (H % 4 == 0);
+    bool fuse = true;   // update_pack picks 16 / 8 / 4-byte accesses from the matrix width and alignment
     for (int i = 0; i < tl.count && fuse; ++i)
-        fuse = ((((uintptr_t)tl.p[i]) | ((uintptr_t)tl.g[i])) & 15) == 0;
+        fuse = ((((uintptr_t)tl.p[i]) | ((uintptr_t)tl.g[i])) & 3) == 0;
     ProfScope ps(c, ZRB_PROF_CLIP_SGD, s);
     if (!fuse) {
         ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, s));

@@ -14,107 +14,133 @@ struct PackSpec {
     int bUC, bG, bKc;
 };
 
-// matrix [rows, cols] (cols % 4 == 0): g *= coef; p -= lr*g; images of the new p.
-// For the recurrent images rows = 4H (gate q = row / H, unit j = row % H), cols = H.
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+    typename VecT<VEC>::type t = __ldcs(reinterpret_cast<const typename VecT<VEC>::type*>(p));
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = f[i];
+}
+// VEC consecutive fp16 values (VEC-element aligned destination) with the widest stores
+template <int VEC>
+__device__ __forceinline__ void store_halves(__half* dst, const __half (&h)[VEC]) {
+    if constexpr (VEC == 1) {
+        dst[0] = h[0];
+    } else {
+#pragma unroll
+        for (int x = 0; x < VEC; x += 2) reinterpret_cast<__half2*>(dst)[x >> 1] = __halves2half2(h[x], h[x + 1]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
+    typename VecT<VEC>::type t;
+    float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) f[i] = v[i];
+    __stcs(reinterpret_cast<typename VecT<VEC>::type*>(p), t);
+}
+
+// matrix [rows, cols] (cols % VEC == 0): g *= coef; p -= lr*g; row-major fp16 image of the new p.
+template <int VEC>
 __global__ void update_pack_kernel(float* __restrict__ p, float* __restrict__ g, int rows, int cols, float lr,
                                    const float* __restrict__ scalars, PackSpec sp) {
     const float coef = scalars[1];
-    const int c4 = cols >> 2;
-    const int64_t total = (int64_t)rows * c4;
-    const int H = cols;
+    const int cv = cols / VEC;
+    const int64_t total = (int64_t)rows * cv;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / c4), c = (int)(i % c4) << 2;
-        float4* g4 = reinterpret_cast<float4*>(g + (int64_t)r * cols + c);
-        float4* p4 = reinterpret_cast<float4*>(p + (int64_t)r * cols + c);
-        float4 gv = __ldcs(g4), pv = __ldcs(p4);
-        gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;
-        pv.x -= lr * gv.x; pv.y -= lr * gv.y; pv.z -= lr * gv.z; pv.w -= lr * gv.w;
-        __stcs(g4, gv);
-        __stcs(p4, pv);
-        const __half h0 = __float2half_rn(pv.x), h1 = __float2half_rn(pv.y), h2 = __float2half_rn(pv.z),
-                     h3 = __float2half_rn(pv.w);
+        const int r = (int)(i / cv), c = (int)(i % cv) * VEC;
+        const int64_t off = (int64_t)r * cols + c;
+        float gv[VEC], pv[VEC];
+        load_vec<VEC>(g + off, gv);
+        load_vec<VEC>(p + off, pv);
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) { gv[x] *= coef; pv[x] -= lr * gv[x]; }
+        store_vec<VEC>(g + off, gv);
+        store_vec<VEC>(p + off, pv);
         if (sp.row_img) {
-            __half2* d = reinterpret_cast<__half2*>(sp.row_img + (int64_t)r * sp.ld + c);
-            d[0] = __halves2half2(h0, h1);
-            d[1] = __halves2half2(h2, h3);
-        }
-        if (sp.fwd_img) {   // W_hh[q*H + j, k..k+3] -> slice of the CTA owning unit j, row 4u+q, K chunk k/8
-            const int q = r / H, j = r % H, k = c;
-            const int cta = j / sp.fU, u = j % sp.fU, row = 4 * u + q;
-            const int64_t idx = (((int64_t)cta * sp.fKc + (k >> 3)) * sp.fG + (row >> 3)) * 64 + (row & 7) * 8 + (k & 7);
-            __half2* d = reinterpret_cast<__half2*>(sp.fwd_img + idx);
-            d[0] = __halves2half2(h0, h1);
-            d[1] = __halves2half2(h2, h3);
-        }
-        if (sp.bwd_img) {   // W_hh[q*H + j, units c..c+3] -> cluster owning those units, rank q, K index j
-            const int q = r / H, j = r % H;
-            const int cl = c / sp.bUC, u = c % sp.bUC;
-            const int64_t base = ((((int64_t)cl * 4 + q) * sp.bKc + (j >> 3)) * sp.bG) * 64 + (j & 7);
-            sp.bwd_img[base + ((u + 0) >> 3) * 64 + ((u + 0) & 7) * 8] = h0;
-            sp.bwd_img[base + ((u + 1) >> 3) * 64 + ((u + 1) & 7) * 8] = h1;
-            sp.bwd_img[base + ((u + 2) >> 3) * 64 + ((u + 2) & 7) * 8] = h2;
-            sp.bwd_img[base + ((u + 3) >> 3) * 64 + ((u + 3) & 7) * 8] = h3;
+            __half hh[VEC];
+#pragma unroll
+            for (int x = 0; x < VEC; ++x) hh[x] = __float2half_rn(pv[x]);
+            store_halves<VEC>(sp.row_img + (int64_t)r * sp.ld + c, hh);
         }
     }
 }
 
-// W_hh [4H, H] with both recurrent images: a thread owns an 8-row x 4-column tile (rows j..j+7 of one gate
+// W_hh [4H, H] with both recurrent images: a thread owns an 8-row x VEC-column tile (rows j..j+7 of one gate
 // block), so the backward image -- whose 16-byte vectors hold 8 consecutive K indices (= rows) of one unit
 // (= column) -- is written with full 16-byte stores instead of 2-byte scatters.
+template <int VEC>
 __global__ void update_pack_whh_kernel(float* __restrict__ p, float* __restrict__ g, int H, float lr,
                                        const float* __restrict__ scalars, PackSpec sp) {
     const float coef = scalars[1];
-    const int c4 = H >> 2, jb_n = (H + 7) >> 3;
-    const int64_t total = (int64_t)4 * jb_n * c4;
+    const int cv = H / VEC, jb_n = (H + 7) >> 3;
+    const int64_t total = (int64_t)4 * jb_n * cv;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % c4) << 2;
-        const int jb = (int)((i / c4) % jb_n), q = (int)(i / ((int64_t)c4 * jb_n));
+        const int c = (int)(i % cv) * VEC;
+        const int jb = (int)((i / cv) % jb_n), q = (int)(i / ((int64_t)cv * jb_n));
         const int j0 = jb << 3;
-        __half hv[8][4];
+        __half hv[8][VEC];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int j = j0 + e;
             if (j < H) {
                 const int64_t off = ((int64_t)q * H + j) * H + c;
-                float4* g4 = reinterpret_cast<float4*>(g + off);
-                float4* p4 = reinterpret_cast<float4*>(p + off);
-                float4 gv = __ldcs(g4), pv = __ldcs(p4);
-                gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;
-                pv.x -= lr * gv.x; pv.y -= lr * gv.y; pv.z -= lr * gv.z; pv.w -= lr * gv.w;
-                __stcs(g4, gv);
-                __stcs(p4, pv);
-                hv[e][0] = __float2half_rn(pv.x); hv[e][1] = __float2half_rn(pv.y);
-                hv[e][2] = __float2half_rn(pv.z); hv[e][3] = __float2half_rn(pv.w);
-                if (sp.row_img) {
-                    __half2* d = reinterpret_cast<__half2*>(sp.row_img + ((int64_t)q * H + j) * sp.ld + c);
-                    d[0] = __halves2half2(hv[e][0], hv[e][1]);
-                    d[1] = __halves2half2(hv[e][2], hv[e][3]);
-                }
-                if (sp.fwd_img) {   // slice of the CTA owning unit j, row 4u+q, K chunk c/8, 4 consecutive K
+                float gv[VEC], pv[VEC];
+                load_vec<VEC>(g + off, gv);
+                load_vec<VEC>(p + off, pv);
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) { gv[x] *= coef; pv[x] -= lr * gv[x]; hv[e][x] = __float2half_rn(pv[x]); }
+                store_vec<VEC>(g + off, gv);
+                store_vec<VEC>(p + off, pv);
+                if (sp.row_img) store_halves<VEC>(sp.row_img + ((int64_t)q * H + j) * sp.ld + c, hv[e]);
+                if (sp.fwd_img) {   // slice of the CTA owning unit j, row 4u+q; K indices c..c+VEC-1 share a K chunk
                     const int cta = j / sp.fU, u = j % sp.fU, row = 4 * u + q;
-                    const int64_t idx = (((int64_t)cta * sp.fKc + (c >> 3)) * sp.fG + (row >> 3)) * 64 + (row & 7) * 8 + (c & 7);
-                    __half2* d = reinterpret_cast<__half2*>(sp.fwd_img + idx);
-                    d[0] = __halves2half2(hv[e][0], hv[e][1]);
-                    d[1] = __halves2half2(hv[e][2], hv[e][3]);
+                    store_halves<VEC>(sp.fwd_img + (((int64_t)cta * sp.fKc + (c >> 3)) * sp.fG + (row >> 3)) * 64 +
+                                          (row & 7) * 8 + (c & 7), hv[e]);
                 }
             } else {
-                hv[e][0] = hv[e][1] = hv[e][2] = hv[e][3] = __float2half_rn(0.f);
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) hv[e][x] = __float2half_rn(0.f);
             }
         }
-        if (sp.bwd_img) {   // units c..c+3 of cluster c/UC, rank q, K chunk jb: one 16-byte vector per unit
-            const int cl = c / sp.bUC, u = c % sp.bUC;
-            const int64_t base = ((((int64_t)cl * 4 + q) * sp.bKc + jb) * sp.bG) * 64;
+        if (sp.bwd_img) {   // units c..c+VEC-1, rank q, K chunk jb: one 16-byte vector per unit
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
+            for (int x = 0; x < VEC; ++x) {
+                const int cl = (c + x) / sp.bUC, u = (c + x) % sp.bUC;
                 uint4 v;
                 v.x = (uint32_t)__half_as_ushort(hv[0][x]) | ((uint32_t)__half_as_ushort(hv[1][x]) << 16);
                 v.y = (uint32_t)__half_as_ushort(hv[2][x]) | ((uint32_t)__half_as_ushort(hv[3][x]) << 16);
                 v.z = (uint32_t)__half_as_ushort(hv[4][x]) | ((uint32_t)__half_as_ushort(hv[5][x]) << 16);
                 v.w = (uint32_t)__half_as_ushort(hv[6][x]) | ((uint32_t)__half_as_ushort(hv[7][x]) << 16);
-                *reinterpret_cast<uint4*>(sp.bwd_img + base + ((u + x) >> 3) * 64 + ((u + x) & 7) * 8) = v;
+                *reinterpret_cast<uint4*>(sp.bwd_img + ((((int64_t)cl * 4 + q) * sp.bKc + jb) * sp.bG) * 64 + (u >> 3) * 64 +
+                                          (u & 7) * 8) = v;
             }
         }
     }
+}
+
+template <int VEC>
+static int update_pack_launch(float* p, float* g, int rows, int cols, float lr, const float* scalars, const PackSpec& sp,
+                              bool whh, cudaStream_t s) {
+    if (whh) {
+        int64_t total = (int64_t)4 * ((cols + 7) / 8) * (cols / VEC);
+        int blocks = (int)((total + 127) / 128);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        update_pack_whh_kernel<VEC><<<blocks, 128, 0, s>>>(p, g, cols, lr, scalars, sp);
+    } else {
+        int64_t total = (int64_t)rows * (cols / VEC);
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        update_pack_kernel<VEC><<<blocks, 256, 0, s>>>(p, g, rows, cols, lr, scalars, sp);
+    }
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
 }
 
 int update_pack(float* p, float* g, int rows, int cols, float lr, const float* scalars, __half* row_img, int64_t ld,
@@ -123,20 +149,11 @@ int update_pack(float* p, float* g, int rows, int cols, float lr, const float* s
     sp.row_img = row_img; sp.ld = ld;
     sp.fwd_img = fwd_img; sp.fU = fp ? fp->U : 1; sp.fG = fp ? fp->G : 1; sp.fKc = fp ? fp->Kc : 1;
     sp.bwd_img = bwd_img; sp.bUC = bp ? 4 * bp->U : 4; sp.bG = bp ? bp->G : 1; sp.bKc = bp ? bp->Kc : 1;
-    if (bwd_img && rows == 4 * cols) {
-        int64_t total = (int64_t)4 * ((cols + 7) / 8) * (cols / 4);
-        int blocks = (int)((total + 127) / 128);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        update_pack_whh_kernel<<<blocks, 128, 0, s>>>(p, g, cols, lr, scalars, sp);
-        ZRB_KERNEL_CHECK();
-        return ZRB_OK;
-    }
-    int64_t total = (int64_t)rows * (cols / 4);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    update_pack_kernel<<<blocks, 256, 0, s>>>(p, g, rows, cols, lr, scalars, sp);
-    ZRB_KERNEL_CHECK();
-    return ZRB_OK;
+    const bool whh = (fwd_img || bwd_img) && rows == 4 * cols;
+    const bool al16 = ((((uintptr_t)p) | ((uintptr_t)g)) & 15) == 0, al8 = ((((uintptr_t)p) | ((uintptr_t)g)) & 7) == 0;
+    if (cols % 4 == 0 && al16) return update_pack_launch<4>(p, g, rows, cols, lr, scalars, sp, whh, s);
+    if (cols % 2 == 0 && al8) return update_pack_launch<2>(p, g, rows, cols, lr, scalars, sp, whh, s);
+    return update_pack_launch<1>(p, g, rows, cols, lr, scalars, sp, whh, s);
 }
 
 }  // namespace zrb

@@ -38,27 +38,38 @@ int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s) {
     return ZRB_OK;
 }
 
-// out[j] = inv_scale * sum_n A[n, j]  for an fp16 matrix with pitch ld
+// out[j] = inv_scale * sum_n A[n, j]  for an fp16 matrix with pitch ld (bias gradients: column sums of dG / dS).
+// A block owns 64 columns (one __half2 per thread in x) and strides the rows with 16 row-lanes in y; fixed-order
+// tree over the row-lanes (deterministic).
 __global__ void colsum_h_kernel(const __half* __restrict__ A, int64_t ld, float* __restrict__ out,
                                 float* __restrict__ out2, int N, int M, float inv_scale) {
-    __shared__ float part[8][33];
-    int col = blockIdx.x * 32 + threadIdx.x;
-    float acc = 0.f;
-    if (col < M)
-        for (int n = threadIdx.y; n < N; n += 8) acc += __half2float(A[(int64_t)n * ld + col]);
-    part[threadIdx.y][threadIdx.x] = acc;
+    __shared__ float part[16][65];
+    const int col = blockIdx.x * 64 + threadIdx.x * 2;
+    float a0 = 0.f, a1 = 0.f;
+    if (col + 1 < M || (col < M && (M & 1) == 0)) {
+        for (int n = threadIdx.y; n < N; n += 16) {
+            __half2 v = *reinterpret_cast<const __half2*>(A + (int64_t)n * ld + col);
+            a0 += __low2float(v);
+            a1 += __high2float(v);
+        }
+    } else if (col < M) {
+        for (int n = threadIdx.y; n < N; n += 16) a0 += __half2float(A[(int64_t)n * ld + col]);
+    }
+    part[threadIdx.y][threadIdx.x * 2] = a0;
+    part[threadIdx.y][threadIdx.x * 2 + 1] = a1;
     __syncthreads();
-    if (threadIdx.y == 0 && col < M) {
-        float t = 0.f;
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    if (t < 64 && blockIdx.x * 64 + t < M) {
+        float s = 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t += part[r][threadIdx.x];
-        out[col] = t * inv_scale;
-        if (out2) out2[col] = t * inv_scale;
+        for (int r = 0; r < 16; ++r) s += part[r][t];
+        out[blockIdx.x * 64 + t] = s * inv_scale;
+        if (out2) out2[blockIdx.x * 64 + t] = s * inv_scale;
     }
 }
 int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, cudaStream_t s) {
-    dim3 blk(32, 8);
-    colsum_h_kernel<<<cdiv(M, 32), blk, 0, s>>>(A, ld, out, out2, N, M, inv_scale);
+    dim3 blk(32, 16);
+    colsum_h_kernel<<<cdiv(M, 64), blk, 0, s>>>(A, ld, out, out2, N, M, inv_scale);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }

@@ -96,8 +96,8 @@ class Trainer:
         self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         # reduce buckets under the rest of backward (1) or all-reduce once after backward (0)
         self.overlap = os.environ.get("ZRB_DP_OVERLAP", "0") == "1"
-        self.ctx = model._context(seq_length, batch_size)
-        _lib.check(_lib.load().zrb_params_changed(self.ctx))
+        self._ctx_cached = None
+        _ = self.ctx
         if self.transport == "ce":
             H, N = model.hidden_size, batch_size * seq_length
             self._rows = torch.zeros(N, H, device=dev)
@@ -160,6 +160,16 @@ class Trainer:
                                               _lib.ptr(self._rows_all), self.world * N, st))
         _lib.check(lib.zrb_dp_finish_step(self._dp, st))
         _lib.check(lib.zrb_set_embed_rows_out(self.ctx, None))
+
+    @property
+    def ctx(self):
+        """The model's library context (re-fetched every call: the model re-creates it when a larger window is
+        requested, and a fresh context must be told that the weights are new to it)."""
+        c = self.model._context(self.T, self.B)
+        if self._ctx_cached is None or c.value != self._ctx_cached:
+            _lib.check(_lib.load().zrb_params_changed(c))
+            self._ctx_cached = c.value
+        return c
 
     def reset_states(self):
         for h, c in self.states:
