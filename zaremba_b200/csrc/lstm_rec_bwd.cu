@@ -287,9 +287,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             if (tr && tid == 0) a.trace[s * 8 + 6] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
-                __threadfence();
-                fence_proxy_async_all();
-                atomicAdd(a.counter, 1u);
+                grid_counter_arrive(a.counter);
                 if (tr) a.trace[s * 8 + 7] = clock64();
             }
             // off the critical path: row-major image for the batched dgrad / wgrad GEMMs

@@ -212,9 +212,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
                 if (tr) a.trace[t * 8 + 6] = clock64();
-                __threadfence();
-                fence_proxy_async_all();
-                atomicAdd(a.counter, 1u);
+                grid_counter_arrive(a.counter);
                 if (tr) a.trace[t * 8 + 7] = clock64();
             }
             // off the critical path: what backward and the next layer read after this kernel

@@ -45,6 +45,13 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
+// Publish this CTA's global writes of the step and arrive on the grid barrier: one release-RED at gpu scope
+// (the bar.sync before it made the other epilogue threads' writes visible to this thread; release is
+// cumulative).  The consumers' TMA reads are ordered by THEIR acquire + fence.proxy.async.
+__device__ __forceinline__ void grid_counter_arrive(unsigned int* counter) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+
 // spin on a global counter (grid barrier) with acquire semantics and the same bounded wait
 __device__ __forceinline__ void grid_counter_wait(const unsigned int* counter, unsigned int target) {
     uint32_t n = 0;
