@@ -16,6 +16,8 @@
 // Per step and CTA: one 72 KB bulk copy (gate r's dG image), H/16 tcgen05.mma (M=64, N=pad8(B), K=16),
 // a 4-way DSMEM reduction of U*B floats, U*B cell updates, one grid-barrier arrival.
 // Roofline: latency / shared-memory bound like the forward kernel; flops per layer call 8*T*B*H^2.
+#include <stdlib.h>
+
 #include "rec_common.cuh"
 
 namespace zrb {
@@ -389,7 +391,10 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     attrs[1].id = cudaLaunchAttributeCooperative;
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 2;
+    // ZRB_NO_COOP=1: cluster launch without the cooperative attribute (profilers refuse the combination; the
+    // grid of <= 132 CTAs, one per SM, is co-resident on an otherwise idle device anyway)
+    static const bool no_coop = getenv("ZRB_NO_COOP") != nullptr;
+    cfg.numAttrs = no_coop ? 1 : 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
     if (e != cudaSuccess) {
         // some drivers refuse cooperative + cluster together: the grid (<= 132 CTAs, one per SM) is
