@@ -156,6 +156,11 @@ int  zrb_train_step_layer(zrb_ctx* ctx, const zrb_params* p, const zrb_params* g
  * dense gradient: rows with equal id are summed in index order by the first occurrence, without atomics, so
  * all ranks get identical bits.  Pass NULL to return to the dense scatter. */
 int  zrb_set_embed_rows_out(zrb_ctx* ctx, float* rows);
+/* Single-process fused step (zrb_train_step_grads/_update with the SAME grads buffers every step): touch only
+ * this window's rows of the dense embedding gradient (clear the previous window's rows instead of zero-filling
+ * 60 MB, take the norm over and update only the rows that can be non-zero).  The dense buffer stays exactly
+ * what the full version would produce.  Not for data parallel runs that all-reduce the dense buffer. */
+int  zrb_set_embed_sparse(zrb_ctx* ctx, int32_t on);
 int  zrb_embed_scatter_rows(zrb_ctx* ctx, float* grad_embed, const int64_t* ids, const float* rows,
                             int64_t n_rows, void* stream);
 int  zrb_train_step_update(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,

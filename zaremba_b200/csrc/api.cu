@@ -114,6 +114,8 @@ int zrb_ctx_create(const zrb_config* cfg, zrb_ctx** out) {
     if (rc == ZRB_OK) rc = dalloc(c, &c->partials, 4096);
     if (rc == ZRB_OK) rc = dalloc(c, &c->scalars, 16);
     if (rc == ZRB_OK) rc = dalloc(c, &c->x_saved, N);
+    if (rc == ZRB_OK) rc = dalloc(c, &c->emb_prev_ids, N);
+    if (rc == ZRB_OK) rc = dalloc(c, &c->emb_first, (size_t)V);
     if (rc == ZRB_OK) rc = dalloc(c, &c->y_dev, N);
     if (rc == ZRB_OK) rc = dalloc(c, &c->x_dev, N);
     if (rc == ZRB_OK) rc = dalloc(c, &c->scores, N * V);
@@ -265,6 +267,13 @@ int zrb_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, i
     return ZRB_OK;
 }
 
+int zrb_set_embed_sparse(zrb_ctx* c, int32_t on) {
+    ZRB_REQUIRE(c, "null ctx");
+    c->emb_sparse = on != 0;
+    c->emb_prev_grad = nullptr;
+    return ZRB_OK;
+}
+
 int zrb_set_embed_rows_out(zrb_ctx* c, float* rows) {
     ZRB_REQUIRE(c, "null ctx");
     c->embed_rows_out = rows;
@@ -276,7 +285,6 @@ int zrb_embed_scatter_rows(zrb_ctx* c, float* grad_embed, const int64_t* ids, co
     ZRB_REQUIRE(c && grad_embed && ids && rows && n_rows >= 0, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     if (n_rows > c->emb_cap_rows) {
-        if (!c->emb_first) ZRB_TRY(dalloc(c, &c->emb_first, (size_t)c->cfg.vocab));
         ZRB_TRY(dalloc(c, &c->emb_acc, (size_t)n_rows * c->cfg.hidden));   // (a previous, smaller one is kept until destroy)
         c->emb_cap_rows = n_rows;
     }

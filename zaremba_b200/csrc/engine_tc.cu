@@ -250,8 +250,17 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
     if (l > 0) return ZRB_OK;
     ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);
     if (c->embed_rows_out) return embed_rows(dY, c->embed_rows_out, N, H, site_mask(c, 0), s);
-    ZRB_CUDA(cudaMemsetAsync(g->embed_w, 0, (size_t)V * H * sizeof(float), s));
+    if (c->emb_sparse && c->emb_prev_grad == g->embed_w) {
+        ZRB_TRY(embed_zero_rows(g->embed_w, c->emb_prev_ids, c->emb_prev_n, H, V, s));   // only last window's rows are non-zero
+    } else {
+        ZRB_CUDA(cudaMemsetAsync(g->embed_w, 0, (size_t)V * H * sizeof(float), s));
+    }
     ZRB_TRY(embed_dropout_bwd(dY, c->x_saved, g->embed_w, N, H, V, site_mask(c, 0), s));
+    if (c->emb_sparse) {
+        ZRB_CUDA(cudaMemcpyAsync(c->emb_prev_ids, c->x_saved, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+        c->emb_prev_n = N;
+        c->emb_prev_grad = g->embed_w;
+    }
     return ZRB_OK;
 }
 
@@ -326,12 +335,24 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
         c->weights_version++;
         return ZRB_OK;
     }
-    ZRB_TRY(grad_norm(tl, max_norm, c->partials, c->scalars, norm_out, s));
     // tensor order of param_list(): embed, (w_ih, w_hh, b_ih, b_hh) x L, fc_w, fc_b
+    const bool rows_only = c->emb_sparse && c->emb_prev_grad == tl.g[0] && c->emb_prev_n > 0;
+    if (rows_only) {
+        // embedding: only the rows of the last window can be non-zero -> norm and update over those rows
+        TensorList dense = tl;
+        dense.n[0] = 0;
+        ZRB_TRY(embed_first_table(c->emb_prev_ids, c->emb_first, c->emb_prev_n, V, s));
+        ZRB_TRY(embed_rows_sumsq(tl.g[0], c->emb_prev_ids, c->emb_first, c->emb_prev_n, H, V,
+                                 c->partials + norm_partials_base(), kNormExtra, s));
+        ZRB_TRY(grad_norm(dense, max_norm, c->partials, c->scalars, norm_out, s, true));
+        ZRB_TRY(embed_rows_update(tl.p[0], tl.g[0], c->emb_prev_ids, c->emb_first, c->emb_prev_n, H, V, lr, c->scalars, s));
+    } else {
+        ZRB_TRY(grad_norm(tl, max_norm, c->partials, c->scalars, norm_out, s));
+    }
     TensorList rest;
     rest.count = 0;
     auto push = [&](int i) { rest.p[rest.count] = tl.p[i]; rest.g[rest.count] = tl.g[i]; rest.n[rest.count] = tl.n[i]; rest.count++; };
-    push(0);
+    if (!rows_only) push(0);
     const bool persistent = t->fplan.ok && t->bplan.ok;
     for (int l = 0; l < L; ++l) {
         const int b = 1 + 4 * l;

@@ -33,6 +33,12 @@ int softmax_nll(const float* scores, const int64_t* y, int N, int V, int B, floa
 int embed_rows(const float* dA, float* rows, int N, int H, MaskSrc m, cudaStream_t s);
 int embed_scatter_rows(const int64_t* ids, const float* rows, float* dW, int n_rows, int H, int V, int* first,
                        long long* acc, cudaStream_t s);
+int embed_zero_rows(float* dW, const int64_t* ids, int n, int H, int V, cudaStream_t s);
+int embed_first_table(const int64_t* ids, int* first, int n, int V, cudaStream_t s);
+int embed_rows_sumsq(const float* dW, const int64_t* ids, const int* first, int n, int H, int V, float* partial,
+                     int nblocks, cudaStream_t s);
+int embed_rows_update(float* W, float* dW, const int64_t* ids, const int* first, int n, int H, int V, float lr,
+                      const float* scalars, cudaStream_t s);
 int dropout_mask_bytes(MaskSrc m, int64_t n, uint8_t* out, cudaStream_t s);
 
 // ---- optim.cu ----------------------------------------------------------------------------
@@ -43,8 +49,11 @@ struct TensorList {
     int count;
 };
 // partials: >= 1024 floats scratch; scalars: >= 4 floats (norm, coef)
+constexpr int kNormExtra = 64;   // extra partial slots after the kNormBlocks ones (embedding rows' sum of squares)
+int norm_partials_base();        // index of the first extra slot
+// extra_used: the caller filled partials[norm_partials_base() .. +kNormExtra) itself (else they are zeroed here)
 int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,
-              cudaStream_t s);
+              cudaStream_t s, bool extra_used = false);
 int sgd_apply(const TensorList& tl, float lr, const float* scalars, cudaStream_t s);
 int clip_sgd(const TensorList& tl, float lr, float max_norm, float* partials, float* scalars, float* norm_out,
              cudaStream_t s);

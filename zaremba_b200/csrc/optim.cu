@@ -125,16 +125,18 @@ static int blocks_for(int64_t n) {
     return (int)(b > kNormBlocks ? kNormBlocks : b);
 }
 
+int norm_partials_base() { return kNormBlocks; }
+
 int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,
-              cudaStream_t s) {
+              cudaStream_t s, bool extra_used) {
     float* p[16]; float* g[16]; int64_t n[16];
     int runs = coalesce(tl, p, g, n);
-    ZRB_CUDA(cudaMemsetAsync(partials, 0, kNormBlocks * sizeof(float), s));
+    ZRB_CUDA(cudaMemsetAsync(partials, 0, (kNormBlocks + (extra_used ? 0 : kNormExtra)) * sizeof(float), s));
     for (int r = 0; r < runs; ++r) {
         sumsq_kernel<<<blocks_for(n[r]), kThreads, 0, s>>>(g[r], n[r], partials, 1);
         ZRB_KERNEL_CHECK();
     }
-    norm_finalize_kernel<<<1, 256, 0, s>>>(partials, kNormBlocks, max_norm, scalars, norm_out);
+    norm_finalize_kernel<<<1, 256, 0, s>>>(partials, kNormBlocks + kNormExtra, max_norm, scalars, norm_out);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }

@@ -349,6 +349,77 @@ int embed_scatter_rows(const int64_t* ids, const float* rows, float* dW, int n_r
     return ZRB_OK;
 }
 
+// ---- touched-rows-only handling of the embedding gradient (single process) ---------------------------------
+// The dense [V,H] gradient is non-zero only in the <= N rows of this window's tokens.  Instead of zero-filling,
+// norm-reading and updating 60 MB per step, only those rows are touched: rows of the PREVIOUS step are cleared,
+// the first occurrence of every id (atomicMin table) owns the row for the norm and the update.
+__global__ void embed_zero_rows_kernel(float* __restrict__ dW, const int64_t* __restrict__ ids, int n, int H, int V) {
+    const int64_t id = ids[blockIdx.x];
+    if (id < 0 || id >= V) return;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) dW[id * (int64_t)H + j] = 0.f;
+}
+int embed_zero_rows(float* dW, const int64_t* ids, int n, int H, int V, cudaStream_t s) {
+    if (!n) return ZRB_OK;
+    embed_zero_rows_kernel<<<n, 256, 0, s>>>(dW, ids, n, H, V);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+int embed_first_table(const int64_t* ids, int* first, int n, int V, cudaStream_t s) {
+    ZRB_CUDA(cudaMemsetAsync(first, 0x7f, (size_t)V * sizeof(int), s));
+    if (!n) return ZRB_OK;
+    embed_first_kernel<<<cdiv(n, 256), 256, 0, s>>>(ids, first, n, V);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+// partial[blockIdx.x] = sum of squares of the rows owned by this block's tokens (first occurrences only)
+__global__ void embed_rows_sumsq_kernel(const float* __restrict__ dW, const int64_t* __restrict__ ids,
+                                        const int* __restrict__ first, int n, int H, int V, float* __restrict__ partial) {
+    __shared__ float sh[8];
+    float acc = 0.f;
+    for (int t = blockIdx.x; t < n; t += gridDim.x) {
+        const int64_t id = ids[t];
+        if (id < 0 || id >= V || first[id] != t) continue;
+        for (int j = threadIdx.x; j < H; j += blockDim.x) {
+            float v = dW[id * (int64_t)H + j];
+            acc += v * v;
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+        partial[blockIdx.x] = t;
+    }
+}
+int embed_rows_sumsq(const float* dW, const int64_t* ids, const int* first, int n, int H, int V, float* partial,
+                     int nblocks, cudaStream_t s) {
+    embed_rows_sumsq_kernel<<<nblocks, 256, 0, s>>>(dW, ids, first, n, H, V, partial);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+__global__ void embed_rows_update_kernel(float* __restrict__ W, float* __restrict__ dW, const int64_t* __restrict__ ids,
+                                         const int* __restrict__ first, int n, int H, int V, float lr,
+                                         const float* __restrict__ scalars) {
+    const int t = blockIdx.x;
+    const int64_t id = ids[t];
+    if (id < 0 || id >= V || first[id] != t) return;
+    const float coef = scalars[1];
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float g = dW[id * (int64_t)H + j] * coef;
+        dW[id * (int64_t)H + j] = g;
+        W[id * (int64_t)H + j] -= lr * g;
+    }
+}
+int embed_rows_update(float* W, float* dW, const int64_t* ids, const int* first, int n, int H, int V, float lr,
+                      const float* scalars, cudaStream_t s) {
+    if (!n) return ZRB_OK;
+    embed_rows_update_kernel<<<n, 256, 0, s>>>(W, dW, ids, first, n, H, V, lr, scalars);
+    ZRB_KERNEL_CHECK();
+    return ZRB_OK;
+}
+
 __global__ void dropout_mask_kernel(MaskSrc m, int64_t n, uint8_t* __restrict__ out) {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (4 * g >= n) return;

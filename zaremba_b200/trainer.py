@@ -98,6 +98,9 @@ class Trainer:
         self.overlap = os.environ.get("ZRB_DP_OVERLAP", "0") == "1"
         self._ctx_cached = None
         _ = self.ctx
+        # single process: the fused step owns the gradient buffers -> touch only the window's embedding rows
+        self._embed_sparse = self.world == 1 and os.environ.get("ZRB_EMBED_SPARSE", "1") == "1"
+        _lib.check(_lib.load().zrb_set_embed_sparse(self.ctx, 1 if self._embed_sparse else 0))
         if self.transport == "ce":
             H, N = model.hidden_size, batch_size * seq_length
             self._rows = torch.zeros(N, H, device=dev)
@@ -168,6 +171,7 @@ class Trainer:
         c = self.model._context(self.T, self.B)
         if self._ctx_cached is None or c.value != self._ctx_cached:
             _lib.check(_lib.load().zrb_params_changed(c))
+            _lib.check(_lib.load().zrb_set_embed_sparse(c, 1 if getattr(self, "_embed_sparse", False) else 0))
             self._ctx_cached = c.value
         return c
 
