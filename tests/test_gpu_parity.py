@@ -407,3 +407,23 @@ def test_sparse_embedding_gradient_rows_and_scatter():
         outs.append(g.clone())
     assert torch.equal(outs[0], outs[1])
     np.testing.assert_allclose(outs[0].cpu().numpy(), want, rtol=2e-6, atol=1e-9)
+
+
+def test_per_timestep_fallback_for_wide_batches():
+    """B > 32 does not fit the persistent recurrence kernels (TMEM accumulator / staging sized for N <= 32):
+    the tcgen05 engine must fall back to one GEMM + one cell launch per timestep and still match the oracle."""
+    import zaremba_b200
+    V, H, L, T, B = 83, 64, 2, 4, 40
+    torch.manual_seed(4)
+    m = zaremba_b200.Model(V, H, L, 0.0, 0.2, engine="tc").to(_dev())
+    m.train()
+    rng = np.random.default_rng(6)
+    x = torch.tensor(rng.integers(0, V, size=(T, B))); y = torch.tensor(rng.integers(0, V, size=(T, B)))
+    scores, _ = m(x, m.state_init(B))
+    _caller_nll_loss(scores, y).backward()
+    params = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in m.named_parameters()}
+    sc, _, cache = O.model_fwd(params, x.numpy(), O.zero_states(L, B, H, np.float64), L)
+    grads = O.model_bwd(params, cache, O.nll_loss_bwd(sc, y.numpy()), L)
+    _scale_close(scores.detach().cpu().numpy(), sc, TOL["tc"]["fwd"], "scores (B=40)")
+    for k, prm in m.named_parameters():
+        _scale_close(prm.grad.cpu().numpy(), grads[k], TOL["tc"]["grad"], f"grad {k} (B=40)")
