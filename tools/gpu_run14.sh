@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-ZRB_NO_COOP=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_bwd_kernel -s 2 -c 2 -f -o gpurun_out/prof_lstm_rec_bwd_kernel python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_lstm_rec_bwd_kernel.log 2>&1; echo "ncu bwd rc=$?"; tail -4 gpurun_out/ncu_lstm_rec_bwd_kernel.log
-ZRB_NO_COOP=1 timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.readline()); print('nocoop', d['ms_per_step'], d['roofline']['class_ms_per_step']['rec_bwd'])"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline > gpurun_out/bench_tc_v10.json 2> gpurun_out/bench_tc_v10.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_tc_v10.json')); print('large', round(d['ms_per_step'],4), round(d['value']), d['roofline']['class_ms_per_step'])"; tail -2 gpurun_out/bench_tc_v10.err
+timeout 300 python tools/bench_dropin.py large > gpurun_out/dropin_large.json 2> gpurun_out/dropin_large.err; cat gpurun_out/dropin_large.json; tail -3 gpurun_out/dropin_large.err
+timeout 300 python tools/bench_dropin.py medium > gpurun_out/dropin_medium.json 2> gpurun_out/dropin_medium.err; cat gpurun_out/dropin_medium.json

@@ -343,7 +343,7 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
         dense.n[0] = 0;
         ZRB_TRY(embed_first_table(c->emb_prev_ids, c->emb_first, c->emb_prev_n, V, s));
         ZRB_TRY(embed_rows_sumsq(tl.g[0], c->emb_prev_ids, c->emb_first, c->emb_prev_n, H, V,
-                                 c->partials + norm_partials_base(), kNormExtra, s));
+                                 c->partials + norm_partials_base(), kNormExtra, s));   // one token per block
         ZRB_TRY(grad_norm(dense, max_norm, c->partials, c->scalars, norm_out, s, true));
         ZRB_TRY(embed_rows_update(tl.p[0], tl.g[0], c->emb_prev_ids, c->emb_first, c->emb_prev_n, H, V, lr, c->scalars, s));
     } else {

@@ -49,7 +49,7 @@ struct TensorList {
     int count;
 };
 // partials: >= 1024 floats scratch; scalars: >= 4 floats (norm, coef)
-constexpr int kNormExtra = 64;   // extra partial slots after the kNormBlocks ones (embedding rows' sum of squares)
+constexpr int kNormExtra = 1024;   // extra partial slots after the kNormBlocks ones (embedding rows' sum of squares)
 int norm_partials_base();        // index of the first extra slot
 // extra_used: the caller filled partials[norm_partials_base() .. +kNormExtra) itself (else they are zeroed here)
 int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,

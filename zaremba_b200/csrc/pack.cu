@@ -39,21 +39,23 @@ int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s) {
 }
 
 // out[j] = inv_scale * sum_n A[n, j]  for an fp16 matrix with pitch ld (bias gradients: column sums of dG / dS).
-// A block owns 64 columns (one __half2 per thread in x) and strides the rows with 16 row-lanes in y; fixed-order
-// tree over the row-lanes (deterministic).
-__global__ void colsum_h_kernel(const __half* __restrict__ A, int64_t ld, float* __restrict__ out,
-                                float* __restrict__ out2, int N, int M, float inv_scale) {
+// Pass 1: block (x, y) owns 64 columns and every kRowSplit-th slab of rows (16 row-lanes, one __half2 per
+// thread) and writes a partial; pass 2 adds the kRowSplit partials in fixed order (deterministic).
+constexpr int kRowSplit = 8;
+__global__ void colsum_h_partial_kernel(const __half* __restrict__ A, int64_t ld, float* __restrict__ part_out, int N,
+                                        int M, int Mp) {
     __shared__ float part[16][65];
     const int col = blockIdx.x * 64 + threadIdx.x * 2;
+    const int rows_per = (N + kRowSplit - 1) / kRowSplit;
+    const int n0 = blockIdx.y * rows_per, n1 = min(N, n0 + rows_per);
     float a0 = 0.f, a1 = 0.f;
-    if (col + 1 < M || (col < M && (M & 1) == 0)) {
-        for (int n = threadIdx.y; n < N; n += 16) {
+    if (col < M) {   // the pitch is even and >= M, so the __half2 read stays inside the row
+#pragma unroll 4
+        for (int n = n0 + threadIdx.y; n < n1; n += 16) {
             __half2 v = *reinterpret_cast<const __half2*>(A + (int64_t)n * ld + col);
             a0 += __low2float(v);
             a1 += __high2float(v);
         }
-    } else if (col < M) {
-        for (int n = threadIdx.y; n < N; n += 16) a0 += __half2float(A[(int64_t)n * ld + col]);
     }
     part[threadIdx.y][threadIdx.x * 2] = a0;
     part[threadIdx.y][threadIdx.x * 2 + 1] = a1;
@@ -63,13 +65,32 @@ __global__ void colsum_h_kernel(const __half* __restrict__ A, int64_t ld, float*
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < 16; ++r) s += part[r][t];
-        out[blockIdx.x * 64 + t] = s * inv_scale;
-        if (out2) out2[blockIdx.x * 64 + t] = s * inv_scale;
+        part_out[(int64_t)blockIdx.y * Mp + blockIdx.x * 64 + t] = s;
     }
 }
+__global__ void colsum_h_final_kernel(const float* __restrict__ part, float* __restrict__ out, float* __restrict__ out2,
+                                      int M, int Mp, float inv_scale) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < kRowSplit; ++y) s += part[(int64_t)y * Mp + j];
+    out[j] = s * inv_scale;
+    if (out2) out2[j] = s * inv_scale;
+}
 int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, cudaStream_t s) {
-    dim3 blk(32, 16);
-    colsum_h_kernel<<<cdiv(M, 64), blk, 0, s>>>(A, ld, out, out2, N, M, inv_scale);
+    static float* scratch = nullptr;
+    static int scratch_cols = 0;
+    const int Mp = (M + 63) / 64 * 64;
+    if (Mp > scratch_cols) {   // grown on first use / for a wider matrix; calls of one context share a stream
+        if (scratch) cudaFree(scratch);
+        ZRB_CUDA(cudaMalloc(&scratch, (size_t)kRowSplit * Mp * sizeof(float)));
+        scratch_cols = Mp;
+    }
+    dim3 blk(32, 16), grid(Mp / 64, kRowSplit);
+    colsum_h_partial_kernel<<<grid, blk, 0, s>>>(A, ld, scratch, N, M, Mp);
+    ZRB_KERNEL_CHECK();
+    colsum_h_final_kernel<<<cdiv(M, 256), 256, 0, s>>>(scratch, out, out2, M, Mp, inv_scale);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
