@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     const int ldd = Bp + 1;
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;
-    float* sD = (float*)(sB + b_bytes);  // [2][64][Bp+1] this CTA's partial product (accumulator pairs summed)
+    float* sD = (float*)(sB + b_bytes);  // [64][Bp+1] this CTA's partial product, all issuers' accumulators summed (sized for two)
     uint64_t* bars = (uint64_t*)((uint8_t*)sD + 2 * 64 * ldd * 4);
     uint64_t* bar_a = bars;
     uint64_t* bar_b = bars + 1;                    // [kRecPieces]
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             const int t = T - 1 - s;                      // step being computed; needs dG_{t+1}
             grid_counter_wait(a.counter, (unsigned int)s * a.nCTA);
             if (tr) a.trace[s * 8 + 0] = clock64();
-            fence_proxy_async_all();
+            fence_proxy_async_global();
             const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + rank) * b_bytes;
             for (int pc = 0; pc < kRecPieces; ++pc) {
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
@@ -173,7 +173,6 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         for (int rr = 0; rr < 4; ++rr) part_addr[rr] = mapa_shared(sD_addr, rr);
         const uint32_t bar_part_addr = smem_u32(bar_part);
         const float inv = 1.f / kGradScale;
-        const int quad = warp & 3, half = warp >> 2;
         const size_t img_gate = (size_t)a.Kc * a.GB * 64;
 
         for (int s = 0; s < T; ++s) {
@@ -203,30 +202,31 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 tcgen05_fence_after();
                 if (tr && tid == 0) a.trace[s * 8 + 3] = clock64();
                 // TMEM -> own shared staging: accumulator row i (cluster-local unit) in lane (i%16)+32*(i/16)
-                {   // warp (quad, half): TMEM lanes [32*quad, +32); accumulators half, half+2, ... are summed
-                    for (int c0 = 0; c0 < Bp; c0 += 8) {
-                        // issue every accumulator's load, wait once, then sum (an issuer with no K step leaves its
-                        // accumulator unwritten: skipped by a warp-uniform test)
-                        uint32_t v[kRecMmaWarps / 2][8];
+                {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
+                    // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
+                    // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
+                    for (int task = warp; task < 4 * a.GB; task += kRecEpiWarps) {
+                        const int quad = task & 3, c0 = (task >> 2) * 8;
+                        uint32_t v[kRecMmaWarps][8];
                         const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
 #pragma unroll
-                        for (int ai = 0; ai < kRecMmaWarps / 2; ++ai)
-                            if (half + 2 * ai < ksteps) tmem_ld_32x8(base + (half + 2 * ai) * 32, v[ai]);
+                        for (int ai = 0; ai < kRecMmaWarps; ++ai)
+                            if (ai < ksteps) tmem_ld_32x8(base + ai * 32, v[ai]);
                         tmem_ld_wait();
                         float acc[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
-                        for (int ai = 0; ai < kRecMmaWarps / 2; ++ai)
-                            if (half + 2 * ai < ksteps) {
+                        for (int ai = 0; ai < kRecMmaWarps; ++ai)
+                            if (ai < ksteps) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(v[ai][i]);
                             }
                         if (lane < 16) {
-                        float* dst = sD + (half * 64 + 16 * quad + lane) * ldd + c0;
+                            float* dst = sD + (16 * quad + lane) * ldd + c0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = acc[i];
-                    }
+                            for (int i = 0; i < 8; ++i) dst[i] = acc[i];
+                        }
                     }
                 }
                 tcgen05_fence_before();
@@ -255,14 +255,10 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 float dh = dyv[k];
                 if (s > 0) {
                     const uint32_t off = (uint32_t)(((int)rank * a.U + u) * ldd + b) * 4u;
-                    const uint32_t off2 = off + (uint32_t)(64 * ldd) * 4u;
-                    float pp[8];   // issue all eight DSMEM loads before the first use (each is ~200+ clk)
+                    float pp[4];   // issue all four DSMEM loads before the first use (each is ~200+ clk)
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        pp[2 * rr] = ld_dsmem_f32(part_addr[rr] + off);
-                        pp[2 * rr + 1] = ld_dsmem_f32(part_addr[rr] + off2);
-                    }
-                    float r = ((pp[0] + pp[1]) + (pp[2] + pp[3])) + ((pp[4] + pp[5]) + (pp[6] + pp[7]));
+                    for (int rr = 0; rr < 4; ++rr) pp[rr] = ld_dsmem_f32(part_addr[rr] + off);
+                    float r = (pp[0] + pp[1]) + (pp[2] + pp[3]);
                     dh += r * inv;
                 }
                 const float tc = fast_tanh(ct[k]);

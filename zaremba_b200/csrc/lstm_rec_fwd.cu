@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     const int ldd = Bp + 1;
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;
-    float* sD = (float*)(sB + b_bytes);                       // [2][64][Bp+1] accumulator staging
+    float* sD = (float*)(sB + b_bytes);                       // [64][Bp+1] accumulator staging (sized for two)
     uint64_t* bars = (uint64_t*)((uint8_t*)sD + 2 * 64 * ldd * 4);
     uint64_t* bar_a = bars;        // weight slice landed
     uint64_t* bar_b = bars + 1;    // [kRecPieces] h image pieces of this step landed
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         for (int t = 0; t < a.T; ++t) {
             if (t > 0) grid_counter_wait(a.counter, (unsigned int)t * a.nCTA);
             if (tr) a.trace[t * 8 + 0] = clock64();
-            fence_proxy_async_all();
+            fence_proxy_async_global();
             const uint8_t* img = (const uint8_t*)a.h_img + (size_t)t * b_bytes;
             for (int pc = 0; pc < kRecPieces; ++pc) {
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             int b = cell / a.U, u = cell % a.U;
             creg[k] = (cell < cells && u < nu) ? a.c0[(size_t)b * H + j0 + u] : 0.f;
         }
-        const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant / which accumulator pair
         for (int t = 0; t < a.T; ++t) {
             // prefetch the x-part pre-activations of this step while the MMAs run
             float pre[kRecMaxCell][4];
@@ -153,29 +152,28 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             bounded_mbar_wait(bar_mma, t & 1);
             tcgen05_fence_after();
             if (tr && tid == 0) a.trace[t * 8 + 3] = clock64();
-            // drain: warp (quad, half) sums accumulators 2*half, 2*half+1 of TMEM lanes [32*quad, +32)
-            // into staging buffer `half`; accumulator row i sits in lane (i % 16) + 32 * (i / 16)
-            {   // warp (quad, half): TMEM lanes [32*quad, +32); accumulators half, half+2, ... are summed
-                for (int c0 = 0; c0 < Bp; c0 += 8) {
-                    // issue every accumulator's load, wait once, then sum (an issuer with no K step leaves its
-                    // accumulator unwritten: skipped by a warp-uniform test)
-                    uint32_t v[kRecMmaWarps / 2][8];
+            {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
+                // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
+                // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
+                for (int task = warp; task < 4 * a.GB; task += kRecEpiWarps) {
+                    const int quad = task & 3, c0 = (task >> 2) * 8;
+                    uint32_t v[kRecMmaWarps][8];
                     const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
 #pragma unroll
-                    for (int ai = 0; ai < kRecMmaWarps / 2; ++ai)
-                        if (half + 2 * ai < ksteps) tmem_ld_32x8(base + (half + 2 * ai) * 32, v[ai]);
+                    for (int ai = 0; ai < kRecMmaWarps; ++ai)
+                        if (ai < ksteps) tmem_ld_32x8(base + ai * 32, v[ai]);
                     tmem_ld_wait();
                     float acc[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
-                    for (int ai = 0; ai < kRecMmaWarps / 2; ++ai)
-                        if (half + 2 * ai < ksteps) {
+                    for (int ai = 0; ai < kRecMmaWarps; ++ai)
+                        if (ai < ksteps) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(v[ai][i]);
                         }
                     if (lane < 16) {
-                        float* dst = sD + (half * 64 + 16 * quad + lane) * ldd + c0;
+                        float* dst = sD + (16 * quad + lane) * ldd + c0;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) dst[i] = acc[i];
                     }
@@ -193,11 +191,10 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 o_i[k] = o_f[k] = o_g[k] = o_o[k] = o_h[k] = 0.f;
                 if (!ok) continue;
                 const float* d0 = sD + (4 * u) * ldd + b;
-                const float* d1 = d0 + 64 * ldd;
-                float zi = pre[k][0] + (d0[0] + d1[0]);
-                float zf = pre[k][1] + (d0[ldd] + d1[ldd]);
-                float zg = pre[k][2] + (d0[2 * ldd] + d1[2 * ldd]);
-                float zo = pre[k][3] + (d0[3 * ldd] + d1[3 * ldd]);
+                float zi = pre[k][0] + d0[0];
+                float zf = pre[k][1] + d0[ldd];
+                float zg = pre[k][2] + d0[2 * ldd];
+                float zo = pre[k][3] + d0[3 * ldd];
                 float gi = fast_sigmoid(zi), gf = fast_sigmoid(zf), gg = fast_tanh(zg), go = fast_sigmoid(zo);
                 float c = gf * creg[k] + gi * gg;
                 float h = go * fast_tanh(c);

@@ -52,17 +52,24 @@ __device__ __forceinline__ void grid_counter_arrive(unsigned int* counter) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
 }
 
-// spin on a global counter (grid barrier) with acquire semantics and the same bounded wait
+// spin on a global counter (grid barrier): relaxed polls (a plain L2 round trip each; ld.acquire would add an L1
+// invalidate per poll), one acquire fence after the last arrival was seen; same bounded wait
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void grid_counter_wait(const unsigned int* counter, unsigned int target) {
     uint32_t n = 0;
     long long t0 = 0;
-    while (ld_acquire_gpu(counter) < target) {
+    while (ld_relaxed_gpu(counter) < target) {
         if ((++n & 0x3FFu) == 0) {
             long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > kSpinCycles) asm volatile("trap;");
         }
     }
+    asm volatile("fence.acquire.gpu;" ::: "memory");
 }
 
 }  // namespace zrb
