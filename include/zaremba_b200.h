@@ -161,6 +161,12 @@ int  zrb_set_embed_rows_out(zrb_ctx* ctx, float* rows);
  * 60 MB, take the norm over and update only the rows that can be non-zero).  The dense buffer stays exactly
  * what the full version would produce.  Not for data parallel runs that all-reduce the dense buffer. */
 int  zrb_set_embed_sparse(zrb_ctx* ctx, int32_t on);
+/* clip_grad_norm_ (main.py:115) scales the gradients in place, so after main.py:117 `.grad` holds coef * g.
+ * on = 1 (default): zrb_train_step_update stores coef * g back like the reference.  on = 0: the update still
+ * applies p -= lr * coef * g but leaves the gradient buffers as backward wrote them (the scaled gradients are
+ * dead values -- main.py:109 zeroes them before the next use -- and storing them is 4 of the ~16 bytes per
+ * parameter the update moves).  zrb_clip_sgd always stores them. */
+int  zrb_set_keep_clipped_grads(zrb_ctx* ctx, int32_t on);
 int  zrb_embed_scatter_rows(zrb_ctx* ctx, float* grad_embed, const int64_t* ids, const float* rows,
                             int64_t n_rows, void* stream);
 int  zrb_train_step_update(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,

@@ -144,6 +144,33 @@ def test_fused_trainer_matches_reference(name, engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
+def test_keep_clipped_grads_option(engine):
+    """clip_grad_norm_ (main.py:115) leaves coef * g in .grad.  keep_clipped_grads=True reproduces that;
+    the default skips the dead store: same weights, loss and norm, .grad = the raw gradients."""
+    import zaremba_b200
+    c = StepCase("mid_H72")
+    x = torch.tensor(c.x(0)).to(_dev()).contiguous()
+    y = torch.tensor(c.y(0)).to(_dev()).contiguous()
+    max_norm = 0.5 * c.norm(0)                      # make sure the clip is active (coef = 0.5)
+    res = []
+    for keep in (True, False):
+        m = _model_from_case(c, engine)
+        m.eval()                                    # no dropout: both runs see the same gradients
+        tr = zaremba_b200.Trainer(m, c.B, c.T, keep_clipped_grads=keep)
+        loss, norm = tr.train_step(x, y, c.lr, max_norm)
+        res.append((loss.item(), norm.item(), tr.flat_p.clone(), tr.flat_g.clone()))
+    (l1, n1, p1, g1), (l0, n0, p0, g0) = res
+    # two separate runs: atomics in the embedding scatter may order differently -> last-bit tolerance
+    assert abs(l1 - l0) <= 1e-6 * abs(l0) and abs(n1 - n0) <= 1e-6 * n0, (l1, l0, n1, n0)
+    torch.testing.assert_close(p1, p0, rtol=1e-6, atol=1e-7)
+    coef = min(1.0, max_norm / (n1 + 1e-6))
+    assert coef < 0.75
+    scale = g0.abs().max().item()
+    assert (g1 - g0 * coef).abs().max().item() <= 1e-5 * scale, "kept gradients are coef * raw gradients"
+    assert (g0 - g1).abs().max().item() > 0.1 * scale, "default leaves the raw gradients"
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 def test_host_buffer_step_equals_device_step(engine):
     """zrb_train_step_host (H2D/D2H inside) == device-token step, bit for bit in eval of loss."""
     import zaremba_b200

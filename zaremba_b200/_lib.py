@@ -63,6 +63,7 @@ _SIGNATURES = {
                                        C.c_uint64, _vp, _vp]),
     "zrb_train_step_layer": (C.c_int, [_vp, C.POINTER(ZrbParams), C.POINTER(ZrbParams), C.c_int32, _vp]),
     "zrb_set_embed_sparse": (C.c_int, [_vp, C.c_int32]),
+    "zrb_set_keep_clipped_grads": (C.c_int, [_vp, C.c_int32]),
     "zrb_set_embed_rows_out": (C.c_int, [_vp, _vp]),
     "zrb_embed_scatter_rows": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp]),
     "zrb_train_step_update": (C.c_int, [_vp, C.POINTER(ZrbParams), C.POINTER(ZrbParams), C.c_float, C.c_float,

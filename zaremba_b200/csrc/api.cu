@@ -111,7 +111,7 @@ int zrb_ctx_create(const zrb_config* cfg, zrb_ctx** out) {
     if (rc == ZRB_OK) rc = dalloc(c, &c->dh_rec, BH);
     if (rc == ZRB_OK) rc = dalloc(c, &c->dc, BH);
     if (rc == ZRB_OK) rc = dalloc(c, &c->row_loss, N);
-    if (rc == ZRB_OK) rc = dalloc(c, &c->partials, 4096);
+    if (rc == ZRB_OK) rc = dalloc(c, &c->partials, 4096 + kNormGemm);
     if (rc == ZRB_OK) rc = dalloc(c, &c->scalars, 16);
     if (rc == ZRB_OK) rc = dalloc(c, &c->x_saved, N);
     if (rc == ZRB_OK) rc = dalloc(c, &c->emb_prev_ids, N);
@@ -203,7 +203,7 @@ int zrb_clip_sgd(zrb_ctx* c, int32_t n, float* const* params, float* const* grad
     for (int i = 0; i < n; ++i) {
         tl.p[i] = params[i]; tl.g[i] = grads[i]; tl.n[i] = sizes[i];
     }
-    ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, (cudaStream_t)stream));
+    ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, true, (cudaStream_t)stream));
     c->weights_version++;
     return ZRB_OK;
 }
@@ -267,6 +267,12 @@ int zrb_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, i
     return ZRB_OK;
 }
 
+int zrb_set_keep_clipped_grads(zrb_ctx* c, int32_t on) {
+    ZRB_REQUIRE(c, "null ctx");
+    c->keep_clipped = on != 0;
+    return ZRB_OK;
+}
+
 int zrb_set_embed_sparse(zrb_ctx* c, int32_t on) {
     ZRB_REQUIRE(c, "null ctx");
     c->emb_sparse = on != 0;
@@ -301,7 +307,7 @@ int zrb_train_step_update(zrb_ctx* c, const zrb_params* p, const zrb_params* g, 
     if (c->cfg.engine == ZRB_ENGINE_TC) return tc_update(c, p, tl, lr, max_norm, norm_out, (cudaStream_t)stream);
     {
         ProfScope ps(c, ZRB_PROF_CLIP_SGD, (cudaStream_t)stream);
-        ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, (cudaStream_t)stream));
+        ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, c->keep_clipped, (cudaStream_t)stream));
     }
     c->weights_version++;
     return ZRB_OK;

@@ -46,6 +46,7 @@ struct zrb_ctx {
     int* emb_first = nullptr;              // workspace of zrb_embed_scatter_rows (allocated on first use)
     long long* emb_acc = nullptr;
     int64_t emb_cap_rows = 0;
+    bool keep_clipped = true;              // zrb_train_step_update writes coef * g back into the gradient buffers
     bool emb_sparse = false;               // fused single-process step: touch only this window's embedding rows
     int64_t* emb_prev_ids = nullptr;       // token ids whose gradient rows are non-zero in emb_prev_grad
     int emb_prev_n = 0;

@@ -36,6 +36,11 @@ struct zrb_tc_state {
     __half* w_img_b[ZRB_MAX_LAYERS] = {};
     __half* g_img = nullptr;
     long long* trace = nullptr;   // [2][T][8] clock stamps (zrb_prof_rec_trace)
+    // fused step (zrb_set_embed_sparse): the wgrad GEMMs leave sums of squares of the matrix gradients in
+    // c->partials, so clip_grad_norm_ does not re-read them; valid for the gradient buffers keyed by wg_key
+    bool wg_ok = false;
+    int wg_slots = 0;
+    const float* wg_key = nullptr;
 };
 
 namespace zrb {
@@ -177,6 +182,20 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
     return ZRB_OK;
 }
 
+// next block of sum-of-squares slots for an [M,N] weight gradient, or null when the step does not fuse the norm
+static float* wgrad_sumsq(zrb_ctx* c, int M, int N) {
+    zrb_tc_state* t = c->tc;
+    if (!t->wg_ok) return nullptr;
+    const int n = gemm_f16_tc_sumsq_slots(M, N);
+    if (t->wg_slots + n > kNormGemm) {
+        t->wg_ok = false;   // does not fit: the update takes the norm over the whole buffers instead
+        return nullptr;
+    }
+    float* out = c->partials + norm_partials_base() + kNormExtra + t->wg_slots;
+    t->wg_slots += n;
+    return out;
+}
+
 // backward from the scaled fp16 image dS_h already in place
 // projection backward: afterwards fc.W / fc.b gradients are complete and c->bwd_dy holds d loss / d act[L]
 static int tc_backward_head(zrb_ctx* c, const zrb_params* p, const zrb_params* g, cudaStream_t s) {
@@ -193,7 +212,10 @@ static int tc_backward_head(zrb_ctx* c, const zrb_params* p, const zrb_params* g
         // dA[N,H] = dS[N,V] * W[V,H]       (W image read MN-major)
         ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 0, t->fc_w_h, Hp, 1, dY, H, N, H, V, inv, nullptr, 0, s));
         // dW[V,H] = dS^T[V,N] * A[N,H]     (both operands MN-major: contraction over tokens)
-        ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s));
+        t->wg_ok = c->emb_sparse;
+        t->wg_slots = 0;
+        t->wg_key = g->fc_w;
+        ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s, wgrad_sumsq(c, V, H)));
         ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, nullptr, N, V, inv, s));
     }
     return ZRB_OK;
@@ -238,8 +260,10 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
             ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 0, t->w_ih_h[l], Hp, 1, dX, H, N, H, 4 * H, inv, nullptr, 0, s));
         }
         ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
-        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->x_h[l], Hp, 1, g->w_ih[l], H, 4 * H, H, N, inv, nullptr, 0, s));
-        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->hprev_h[l], Hp, 1, g->w_hh[l], H, 4 * H, H, N, inv, nullptr, 0, s));
+        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->x_h[l], Hp, 1, g->w_ih[l], H, 4 * H, H, N, inv, nullptr, 0, s,
+                            wgrad_sumsq(c, 4 * H, H)));
+        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->hprev_h[l], Hp, 1, g->w_hh[l], H, 4 * H, H, N, inv, nullptr, 0, s,
+                            wgrad_sumsq(c, 4 * H, H)));
         if (t->bplan.ok) ZRB_TRY(colsum_h(t->dG_h, G4p, g->b_ih[l], g->b_hh[l], N, 4 * H, inv, s));
         else ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
         float* tmp = dY; dY = dX; dX = tmp;
@@ -331,7 +355,7 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
         fuse = ((((uintptr_t)tl.p[i]) | ((uintptr_t)tl.g[i])) & 3) == 0;
     ProfScope ps(c, ZRB_PROF_CLIP_SGD, s);
     if (!fuse) {
-        ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, s));
+        ZRB_TRY(clip_sgd(tl, lr, max_norm, c->partials, c->scalars, norm_out, c->keep_clipped, s));
         c->weights_version++;
         return ZRB_OK;
     }
@@ -341,11 +365,17 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
         // embedding: only the rows of the last window can be non-zero -> norm and update over those rows
         TensorList dense = tl;
         dense.n[0] = 0;
+        const bool gemm_norm = t->wg_ok && t->wg_key == tl.g[1 + 4 * L];   // matrices: summed by the wgrad GEMMs
+        if (gemm_norm) {
+            for (int l = 0; l < L; ++l) dense.n[1 + 4 * l] = dense.n[2 + 4 * l] = 0;
+            dense.n[1 + 4 * L] = 0;
+        }
         ZRB_TRY(embed_first_table(c->emb_prev_ids, c->emb_first, c->emb_prev_n, V, s));
         ZRB_TRY(embed_rows_sumsq(tl.g[0], c->emb_prev_ids, c->emb_first, c->emb_prev_n, H, V,
                                  c->partials + norm_partials_base(), kNormExtra, s));   // one token per block
-        ZRB_TRY(grad_norm(dense, max_norm, c->partials, c->scalars, norm_out, s, true));
-        ZRB_TRY(embed_rows_update(tl.p[0], tl.g[0], c->emb_prev_ids, c->emb_first, c->emb_prev_n, H, V, lr, c->scalars, s));
+        ZRB_TRY(grad_norm(dense, max_norm, c->partials, c->scalars, norm_out, s, true, gemm_norm ? t->wg_slots : 0));
+        ZRB_TRY(embed_rows_update(tl.p[0], tl.g[0], c->emb_prev_ids, c->emb_first, c->emb_prev_n, H, V, lr, c->scalars,
+                                  c->keep_clipped, s));
     } else {
         ZRB_TRY(grad_norm(tl, max_norm, c->partials, c->scalars, norm_out, s));
     }
@@ -357,18 +387,20 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
     for (int l = 0; l < L; ++l) {
         const int b = 1 + 4 * l;
         ZRB_TRY(update_pack(tl.p[b], tl.g[b], 4 * H, H, lr, c->scalars, t->w_ih_h[l], t->Hp, nullptr, nullptr, nullptr,
-                            nullptr, s));
+                            nullptr, c->keep_clipped, s));
         ZRB_TRY(update_pack(tl.p[b + 1], tl.g[b + 1], 4 * H, H, lr, c->scalars, persistent ? nullptr : t->w_hh_h[l],
                             t->Hp, t->fplan.ok ? t->w_img_f[l] : nullptr, &t->fplan,
-                            t->bplan.ok ? t->w_img_b[l] : nullptr, &t->bplan, s));
+                            t->bplan.ok ? t->w_img_b[l] : nullptr, &t->bplan, c->keep_clipped, s));
         push(b + 2);
         push(b + 3);
     }
     const int f = 1 + 4 * L;
-    ZRB_TRY(update_pack(tl.p[f], tl.g[f], V, H, lr, c->scalars, t->fc_w_h, t->Hp, nullptr, nullptr, nullptr, nullptr, s));
+    ZRB_TRY(update_pack(tl.p[f], tl.g[f], V, H, lr, c->scalars, t->fc_w_h, t->Hp, nullptr, nullptr, nullptr, nullptr,
+                        c->keep_clipped, s));
     push(f + 1);
-    ZRB_TRY(sgd_apply(rest, lr, c->scalars, s));
+    ZRB_TRY(sgd_apply(rest, lr, c->scalars, c->keep_clipped, s));
     for (int l = 0; l < L; ++l) ZRB_TRY(add_vec(p->b_ih[l], p->b_hh[l], t->bsum[l], 4 * H, s));
+    t->wg_ok = false;
     c->weights_version++;
     t->packed_version = c->weights_version;      // images are current
     t->packed_params = *p;

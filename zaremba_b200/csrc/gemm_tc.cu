@@ -45,6 +45,8 @@ struct GemmArgs {
     int accumulate;
     int tiles_m, tiles_n;
     int splits;      // split-K factor (1 or 2); with 2 the epilogue adds atomically into a zeroed C
+    float* sumsq_out; // or null: slot [tile * 4 + q] = sum of squares of the outputs epilogue warp q stored for `tile`
+                      // (the wgrads feed clip_grad_norm_ from here instead of re-reading 200 MB of gradients)
 };
 
 template <bool A_MN, bool B_MN, int GBN>
@@ -163,6 +165,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             mbar_wait(&acc_full[as], aph);
             tcgen05_fence_after();
             const bool add_bias = p.bias != nullptr && split == 0;
+            float ss = 0.f;
 #pragma unroll 1
             for (int c = 0; c < GBN / 32; ++c) {
                 uint32_t v[32];
@@ -183,7 +186,11 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         } else if (p.accumulate) {
                             for (int r = 0; r < rows; ++r) cptr[(int64_t)r * p.ldc] += sw[r * 33 + lane] + bv;
                         } else {
-                            for (int r = 0; r < rows; ++r) cptr[(int64_t)r * p.ldc] = sw[r * 33 + lane] + bv;
+                            for (int r = 0; r < rows; ++r) {
+                                const float o = sw[r * 33 + lane] + bv;
+                                cptr[(int64_t)r * p.ldc] = o;
+                                ss += o * o;
+                            }
                         }
                     }
                     __syncwarp();
@@ -192,6 +199,10 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (p.sumsq_out) {   // after the release of the accumulator: off the MMA warp's critical path
+                ss = warp_sum(ss);
+                if (lane == 0) p.sumsq_out[tile * 4 + q] = ss;
+            }
             if (++as == kAccStages) { as = 0; aph ^= 1; }
         }
     }
@@ -285,9 +296,17 @@ static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
     return launch_gemm<true, true, GBN>(ta, tb, a, s);
 }
 
+// number of sumsq_out slots gemm_f16_tc writes for an [M,N] output (same tile choice as below)
+int gemm_f16_tc_sumsq_slots(int M, int N) {
+    const int tiles_m = cdiv(M, GBM);
+    const int bn = (tiles_m * cdiv(N, 256) >= (tc_num_sms() * 9) / 10) ? 256 : 128;
+    return tiles_m * cdiv(N, bn) * 4;
+}
+
 int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t ldb, int b_mn, float* C, int64_t ldc,
-                int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s) {
+                int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, float* sumsq_out) {
     if (M <= 0 || N <= 0) return ZRB_OK;
+    ZRB_REQUIRE(!sumsq_out || !accumulate, "sumsq_out needs a plain store epilogue");
     ZRB_REQUIRE(K > 0, "gemm_f16_tc needs K > 0");
     // 128x256 tiles when they still give every SM (nearly) a full wave of work, else 128x128
     const int tiles_m = cdiv(M, GBM);
@@ -303,7 +322,8 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
     // few output tiles but a long contraction (the dgrads: 72 tiles x 94 K blocks): split K in two so
     // that ~all SMs work; two partials added into a zeroed C are order-independent (a+b == b+a)
     a.splits = 1;
-    if (a.tiles_m * a.tiles_n * 2 <= tc_num_sms() && cdiv(K, GBK) >= 8 && ldc == N) {
+    a.sumsq_out = sumsq_out;
+    if (!sumsq_out && a.tiles_m * a.tiles_n * 2 <= tc_num_sms() && cdiv(K, GBK) >= 8 && ldc == N) {
         a.splits = 2;
         if (!accumulate) ZRB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));
     }
@@ -317,5 +337,5 @@ extern "C" int zrb_gemm_f16(const void* A, int64_t lda, int32_t a_mn_major, cons
                             const float* bias, int32_t accumulate, void* stream) {
     ZRB_REQUIRE(A && B && C, "null argument");
     return zrb::gemm_f16_tc((const __half*)A, lda, a_mn_major, (const __half*)B, ldb, b_mn_major, C, ldc, M, N, K,
-                            alpha, bias, accumulate, (cudaStream_t)stream);
+                            alpha, bias, accumulate, (cudaStream_t)stream, nullptr);
 }

@@ -38,7 +38,7 @@ int embed_first_table(const int64_t* ids, int* first, int n, int V, cudaStream_t
 int embed_rows_sumsq(const float* dW, const int64_t* ids, const int* first, int n, int H, int V, float* partial,
                      int nblocks, cudaStream_t s);
 int embed_rows_update(float* W, float* dW, const int64_t* ids, const int* first, int n, int H, int V, float lr,
-                      const float* scalars, cudaStream_t s);
+                      const float* scalars, bool write_g, cudaStream_t s);
 int dropout_mask_bytes(MaskSrc m, int64_t n, uint8_t* out, cudaStream_t s);
 
 // ---- optim.cu ----------------------------------------------------------------------------
@@ -49,14 +49,17 @@ struct TensorList {
     int count;
 };
 // partials: >= 1024 floats scratch; scalars: >= 4 floats (norm, coef)
+constexpr int kNormGemm = 16384;  // then: per-(tile, epilogue warp) sums of squares written by the wgrad GEMMs (tensor-core engine)
 constexpr int kNormExtra = 1024;   // extra partial slots after the kNormBlocks ones (embedding rows' sum of squares)
 int norm_partials_base();        // index of the first extra slot
 // extra_used: the caller filled partials[norm_partials_base() .. +kNormExtra) itself (else they are zeroed here)
+// n_gemm: that many slots after the extra ones hold sums of squares of tensors NOT in `tl` (gemm_f16_tc sumsq_out)
 int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,
-              cudaStream_t s, bool extra_used = false);
-int sgd_apply(const TensorList& tl, float lr, const float* scalars, cudaStream_t s);
+              cudaStream_t s, bool extra_used = false, int n_gemm = 0);
+// write_g: store coef * g back (clip_grad_norm_ scales .grad in place); false leaves the raw gradient
+int sgd_apply(const TensorList& tl, float lr, const float* scalars, bool write_g, cudaStream_t s);
 int clip_sgd(const TensorList& tl, float lr, float max_norm, float* partials, float* scalars, float* norm_out,
-             cudaStream_t s);
+             bool write_g, cudaStream_t s);
 
 // ---- gemm_simt.cu ------------------------------------------------------------------------
 int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, int transA, int transB, float alpha,

@@ -75,6 +75,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partials, int n, 
 }
 
 // g *= coef (clip_grad_norm_ scales .grad in place); p -= lr * g (main.py:117)
+template <bool WRITE_G>
 __global__ void clip_sgd_update_kernel(float* __restrict__ p, float* __restrict__ g, int64_t n, float lr,
                                        const float* __restrict__ scalars) {
     const float coef = scalars[1];
@@ -87,18 +88,18 @@ __global__ void clip_sgd_update_kernel(float* __restrict__ p, float* __restrict_
             float4 gv = __ldcs(g4 + i), pv = __ldcs(p4 + i);
             gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;
             pv.x -= lr * gv.x; pv.y -= lr * gv.y; pv.z -= lr * gv.z; pv.w -= lr * gv.w;
-            __stcs(g4 + i, gv);
+            if (WRITE_G) __stcs(g4 + i, gv);
             __stcs(p4 + i, pv);
         }
         for (int64_t j = (n4 << 2) + tid; j < n; j += stride) {
             float gv = g[j] * coef;
-            g[j] = gv;
+            if (WRITE_G) g[j] = gv;
             p[j] -= lr * gv;
         }
     } else {
         for (int64_t j = tid; j < n; j += stride) {
             float gv = g[j] * coef;
-            g[j] = gv;
+            if (WRITE_G) g[j] = gv;
             p[j] -= lr * gv;
         }
     }
@@ -128,7 +129,7 @@ static int blocks_for(int64_t n) {
 int norm_partials_base() { return kNormBlocks; }
 
 int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,
-              cudaStream_t s, bool extra_used) {
+              cudaStream_t s, bool extra_used, int n_gemm) {
     float* p[16]; float* g[16]; int64_t n[16];
     int runs = coalesce(tl, p, g, n);
     ZRB_CUDA(cudaMemsetAsync(partials, 0, (kNormBlocks + (extra_used ? 0 : kNormExtra)) * sizeof(float), s));
@@ -136,32 +137,27 @@ int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scal
         sumsq_kernel<<<blocks_for(n[r]), kThreads, 0, s>>>(g[r], n[r], partials, 1);
         ZRB_KERNEL_CHECK();
     }
-    norm_finalize_kernel<<<1, 256, 0, s>>>(partials, kNormBlocks + kNormExtra, max_norm, scalars, norm_out);
+    norm_finalize_kernel<<<1, 256, 0, s>>>(partials, kNormBlocks + kNormExtra + n_gemm, max_norm, scalars, norm_out);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
 
 // update only (norm / coefficient already in `scalars`)
-int sgd_apply(const TensorList& tl, float lr, const float* scalars, cudaStream_t s) {
+int sgd_apply(const TensorList& tl, float lr, const float* scalars, bool write_g, cudaStream_t s) {
     float* p[16]; float* g[16]; int64_t n[16];
     int runs = coalesce(tl, p, g, n);
     for (int r = 0; r < runs; ++r) {
-        clip_sgd_update_kernel<<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
+        if (write_g) clip_sgd_update_kernel<true><<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
+        else clip_sgd_update_kernel<false><<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
         ZRB_KERNEL_CHECK();
     }
     return ZRB_OK;
 }
 
 int clip_sgd(const TensorList& tl, float lr, float max_norm, float* partials, float* scalars, float* norm_out,
-             cudaStream_t s) {
+             bool write_g, cudaStream_t s) {
     ZRB_TRY(grad_norm(tl, max_norm, partials, scalars, norm_out, s));
-    float* p[16]; float* g[16]; int64_t n[16];
-    int runs = coalesce(tl, p, g, n);
-    for (int r = 0; r < runs; ++r) {
-        clip_sgd_update_kernel<<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
-        ZRB_KERNEL_CHECK();
-    }
-    return ZRB_OK;
+    return sgd_apply(tl, lr, scalars, write_g, s);
 }
 
 }  // namespace zrb

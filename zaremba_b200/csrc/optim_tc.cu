@@ -12,6 +12,7 @@ struct PackSpec {
     int fU, fG, fKc;
     __half* bwd_img;     // recurrent backward slices [cluster][4][kc][g][8][8] or null
     int bUC, bG, bKc;
+    int write_g;         // store coef * g back into the gradient buffer (clip_grad_norm_'s in-place scaling)
 };
 
 template <int VEC> struct VecT;
@@ -61,7 +62,7 @@ __global__ void update_pack_kernel(float* __restrict__ p, float* __restrict__ g,
         load_vec<VEC>(p + off, pv);
 #pragma unroll
         for (int x = 0; x < VEC; ++x) { gv[x] *= coef; pv[x] -= lr * gv[x]; }
-        store_vec<VEC>(g + off, gv);
+        if (sp.write_g) store_vec<VEC>(g + off, gv);
         store_vec<VEC>(p + off, pv);
         if (sp.row_img) {
             __half hh[VEC];
@@ -96,7 +97,7 @@ __global__ void update_pack_whh_kernel(float* __restrict__ p, float* __restrict_
                 load_vec<VEC>(p + off, pv);
 #pragma unroll
                 for (int x = 0; x < VEC; ++x) { gv[x] *= coef; pv[x] -= lr * gv[x]; hv[e][x] = __float2half_rn(pv[x]); }
-                store_vec<VEC>(g + off, gv);
+                if (sp.write_g) store_vec<VEC>(g + off, gv);
                 store_vec<VEC>(p + off, pv);
                 if (sp.row_img) store_halves<VEC>(sp.row_img + ((int64_t)q * H + j) * sp.ld + c, hv[e]);
                 if (sp.fwd_img) {   // slice of the CTA owning unit j, row 4u+q; K indices c..c+VEC-1 share a K chunk
@@ -144,8 +145,9 @@ static int update_pack_launch(float* p, float* g, int rows, int cols, float lr, 
 }
 
 int update_pack(float* p, float* g, int rows, int cols, float lr, const float* scalars, __half* row_img, int64_t ld,
-                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, cudaStream_t s) {
+                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, bool write_g, cudaStream_t s) {
     PackSpec sp;
+    sp.write_g = write_g ? 1 : 0;
     sp.row_img = row_img; sp.ld = ld;
     sp.fwd_img = fwd_img; sp.fU = fp ? fp->U : 1; sp.fG = fp ? fp->G : 1; sp.fKc = fp ? fp->Kc : 1;
     sp.bwd_img = bwd_img; sp.bUC = bp ? 4 * bp->U : 4; sp.bG = bp ? bp->G : 1; sp.bKc = bp ? bp->Kc : 1;

@@ -401,21 +401,21 @@ int embed_rows_sumsq(const float* dW, const int64_t* ids, const int* first, int 
 }
 __global__ void embed_rows_update_kernel(float* __restrict__ W, float* __restrict__ dW, const int64_t* __restrict__ ids,
                                          const int* __restrict__ first, int n, int H, int V, float lr,
-                                         const float* __restrict__ scalars) {
+                                         const float* __restrict__ scalars, bool write_g) {
     const int t = blockIdx.x;
     const int64_t id = ids[t];
     if (id < 0 || id >= V || first[id] != t) return;
     const float coef = scalars[1];
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         float g = dW[id * (int64_t)H + j] * coef;
-        dW[id * (int64_t)H + j] = g;
+        if (write_g) dW[id * (int64_t)H + j] = g;
         W[id * (int64_t)H + j] -= lr * g;
     }
 }
 int embed_rows_update(float* W, float* dW, const int64_t* ids, const int* first, int n, int H, int V, float lr,
-                      const float* scalars, cudaStream_t s) {
+                      const float* scalars, bool write_g, cudaStream_t s) {
     if (!n) return ZRB_OK;
-    embed_rows_update_kernel<<<n, 256, 0, s>>>(W, dW, ids, first, n, H, V, lr, scalars);
+    embed_rows_update_kernel<<<n, 256, 0, s>>>(W, dW, ids, first, n, H, V, lr, scalars, write_g);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }

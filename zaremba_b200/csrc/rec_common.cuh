@@ -18,7 +18,11 @@ constexpr int kRecTmemCols = 32 * kRecMmaWarps;       // one fp32 accumulator (N
                                                       // ~45 clk floor per instruction for N <= 64 (measured); one issuing
                                                       // thread only reaches ~90 clk (descriptor math + R2UR in series with
                                                       // the issue); 2 threads with private accumulators reach ~57, 4 threads ~33 clk per MMA
-constexpr int kRecPieces = 4;                         // operand image arrives in this many bulk copies
+constexpr int kRecPieces = 4;                         // operand image arrives in this many bulk copies.  (One grid-barrier
+                                                      // counter and loader lane PER PIECE, so that a late CTA only delays the
+                                                      // piece it writes, was measured 5% slower: 4x the polling traffic and a
+                                                      // longer arrival; issuing both drain tasks' TMEM loads before one wait
+                                                      // was also slower than two rounds.)
 constexpr int kRecMaxCell = 2;                        // (unit, batch) cells per epilogue thread
 constexpr long long kSpinCycles = 6000000000ll;  // ~3 s at 2 GHz: a lost wake-up traps instead of hanging the GPU
 

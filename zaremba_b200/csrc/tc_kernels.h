@@ -38,7 +38,7 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, __half* h_img, float* ga
                  int Hp, MaskSrc m, cudaStream_t s, long long* trace = nullptr);
 // SGD update of one matrix fused with its fp16 image rebuild (optim_tc.cu)
 int update_pack(float* p, float* g, int rows, int cols, float lr, const float* scalars, __half* row_img, int64_t ld,
-                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, cudaStream_t s);
+                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, bool write_g, cudaStream_t s);
 int rec_bwd_plan(int H, int B, RecPlan* plan);   // U = units per CTA, nCTA = 4 * clusters
 int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s);
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,

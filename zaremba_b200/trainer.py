@@ -38,7 +38,11 @@ def minibatch(data, batch_size, seq_length):
 
 
 class Trainer:
-    def __init__(self, model: Model, batch_size: int, seq_length: int, process_group=None):
+    def __init__(self, model: Model, batch_size: int, seq_length: int, process_group=None,
+                 keep_clipped_grads: bool = False):
+        """keep_clipped_grads: after a step `.grad` holds coef * g as clip_grad_norm_ (main.py:115) leaves it.  The
+        default skips that store (the values are dead: the next step overwrites them) and `.grad` keeps the raw
+        gradients of the step; weights, loss and norm are the same either way."""
         if model.lstm_type != "pytorch":
             raise ValueError("Trainer drives the --lstm_type pytorch layout")
         dev = model.embed.W.device
@@ -46,6 +50,7 @@ class Trainer:
             raise RuntimeError("Trainer needs the model on a CUDA device (no CPU fallback)")
         self.model, self.B, self.T, self.dev = model, batch_size, seq_length, dev
         self.pg = process_group
+        self._keep_clipped = bool(keep_clipped_grads)
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         params = model.ordered_parameters()
         sizes = [p.numel() for p in params]
@@ -101,6 +106,7 @@ class Trainer:
         # single process: the fused step owns the gradient buffers -> touch only the window's embedding rows
         self._embed_sparse = self.world == 1 and os.environ.get("ZRB_EMBED_SPARSE", "1") == "1"
         _lib.check(_lib.load().zrb_set_embed_sparse(self.ctx, 1 if self._embed_sparse else 0))
+        _lib.check(_lib.load().zrb_set_keep_clipped_grads(self.ctx, 1 if self._keep_clipped else 0))
         if self.transport == "ce":
             H, N = model.hidden_size, batch_size * seq_length
             self._rows = torch.zeros(N, H, device=dev)
@@ -172,6 +178,7 @@ class Trainer:
         if self._ctx_cached is None or c.value != self._ctx_cached:
             _lib.check(_lib.load().zrb_params_changed(c))
             _lib.check(_lib.load().zrb_set_embed_sparse(c, 1 if getattr(self, "_embed_sparse", False) else 0))
+            _lib.check(_lib.load().zrb_set_keep_clipped_grads(c, 1 if self._keep_clipped else 0))
             self._ctx_cached = c.value
         return c
 
