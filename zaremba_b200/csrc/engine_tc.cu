@@ -183,10 +183,10 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
 }
 
 // next block of sum-of-squares slots for an [M,N] weight gradient, or null when the step does not fuse the norm
-static float* wgrad_sumsq(zrb_ctx* c, int M, int N) {
+static float* wgrad_sumsq(zrb_ctx* c, int M, int N, int K) {
     zrb_tc_state* t = c->tc;
     if (!t->wg_ok) return nullptr;
-    const int n = gemm_f16_tc_sumsq_slots(M, N);
+    const int n = gemm_f16_tc_sumsq_slots(M, N, K);
     if (t->wg_slots + n > kNormGemm) {
         t->wg_ok = false;   // does not fit: the update takes the norm over the whole buffers instead
         return nullptr;
@@ -215,7 +215,7 @@ static int tc_backward_head(zrb_ctx* c, const zrb_params* p, const zrb_params* g
         t->wg_ok = c->emb_sparse;
         t->wg_slots = 0;
         t->wg_key = g->fc_w;
-        ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s, wgrad_sumsq(c, V, H)));
+        ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s, wgrad_sumsq(c, V, H, N)));
         ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, nullptr, N, V, inv, s));
     }
     return ZRB_OK;
@@ -261,9 +261,9 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
         }
         ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
         ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->x_h[l], Hp, 1, g->w_ih[l], H, 4 * H, H, N, inv, nullptr, 0, s,
-                            wgrad_sumsq(c, 4 * H, H)));
+                            wgrad_sumsq(c, 4 * H, H, N)));
         ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->hprev_h[l], Hp, 1, g->w_hh[l], H, 4 * H, H, N, inv, nullptr, 0, s,
-                            wgrad_sumsq(c, 4 * H, H)));
+                            wgrad_sumsq(c, 4 * H, H, N)));
         if (t->bplan.ok) ZRB_TRY(colsum_h(t->dG_h, G4p, g->b_ih[l], g->b_hh[l], N, 4 * H, inv, s));
         else ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
         float* tmp = dY; dY = dX; dX = tmp;

@@ -6,14 +6,17 @@
 //   warp 0   TMA producer   : cp.async.bulk.tensor 2-D boxes, 128B swizzle, 6-stage mbarrier ring
 //   warp 1   MMA issuer     : one thread issues tcgen05.mma 128x128x16 (cta_group::1), commits
 //                             to the ring's "empty" barriers and to the accumulator "full" barrier
-//   warp 2   TMEM allocator : 256 columns = two 128x128 fp32 accumulators (epilogue of tile i
-//                             overlaps the MMAs of tile i+1)
-//   warps 4-7 epilogue      : tcgen05.ld 32x32b, alpha/bias, fp32 stores
+//   warp 2   TMEM allocator : two accumulator stages (epilogue of tile i overlaps the MMAs of tile i+1), or, for
+//                             the 256x256 tile (MT = 2: two 128-row accumulators that share every B tile), one
+//                             stage filling all 512 columns
+//   warps 4-11 epilogue     : tcgen05.ld 32x32b, alpha/bias, fp32 stores (two warps per TMEM lane quadrant)
 //
 // Every batched contraction of the path runs here: X*W_ih^T, the vocabulary projection, their
 // dgrads (weights read MN-major from the same fp16 image, no transposed copies) and the
 // wgrads (both operands MN-major: contraction over tokens).  Roofline: tensor pipe
 // (2*M*N*K flop per call); operands stream once from HBM/L2 via TMA.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 #include "tc_host.h"
@@ -23,16 +26,23 @@ namespace zrb {
 using namespace tc;
 
 constexpr int GBM = 128, GBK = 64;
-constexpr int kAccStages = 2;
-constexpr int kABytes = GBM * GBK * 2;
-constexpr int kEpiBytes = 4 * 32 * 33 * 4;   // per-epilogue-warp 32x32 transpose tile (padded)
-constexpr int kGemmThreads = 256;
+constexpr int kASubBytes = GBM * GBK * 2;   // one 128-row A sub-tile of a K block
+constexpr int kEpiWarps = 8;
+constexpr int kEpiBytes = kEpiWarps * 32 * 33 * 4;   // per-epilogue-warp 32x32 transpose tile (padded)
+constexpr int kGemmThreads = (4 + kEpiWarps) * 32;
 // Tile N is a template parameter: 128 (6 stages) or 256 (4 stages).  The kernel is L2->SM bandwidth bound
 // (128x128 tiles pull 32 KB per 2.1 MFLOP K block); 128x256 tiles pull 25% fewer bytes per flop, and their
 // 128-clk MMAs hide the issue latency, so 256 is used whenever it still fills the machine.
-template <int GBN> struct GemmCfg {
-    static constexpr int kStages = GBN == 256 ? 4 : 6;
+// MT = 128-row accumulators per CTA tile.  The kernel is L2->SM bound: per K block a 128x256 tile pulls 48 KB for
+// 4.2 MFLOP, a 256x256 tile (MT = 2) 64 KB for 8.4 MFLOP -- a third less traffic per flop.  Its two accumulators fill
+// TMEM, so the epilogue no longer overlaps the next tile; the shapes of this path give (about) one wave of such
+// tiles anyway (e.g. [700 x 10000]: 120 tiles, [6000 x 1500]: 144 tiles on 148 SMs).
+template <int GBN, int MT> struct GemmCfg {
+    static constexpr int kStages = MT == 2 ? 3 : (GBN == 256 ? 4 : 6);
+    static constexpr int kABytes = MT * kASubBytes;
     static constexpr int kBBytes = GBN * GBK * 2;
+    static constexpr int kAccStages = MT * GBN >= 512 ? 1 : 2;
+    static constexpr int kTmemCols = kAccStages * MT * GBN;
     static constexpr int kSmem = kStages * (kABytes + kBBytes) + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -45,15 +55,19 @@ struct GemmArgs {
     int accumulate;
     int tiles_m, tiles_n;
     int splits;      // split-K factor (1 or 2); with 2 the epilogue adds atomically into a zeroed C
-    float* sumsq_out; // or null: slot [tile * 4 + q] = sum of squares of the outputs epilogue warp q stored for `tile`
+    float* sumsq_out; // or null: slot [tile * 8 + w] = sum of squares of the outputs epilogue warp w stored for `tile`
                       // (the wgrads feed clip_grad_norm_ from here instead of re-reading 200 MB of gradients)
 };
 
-template <bool A_MN, bool B_MN, int GBN>
+template <bool A_MN, bool B_MN, int GBN, int MT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmArgs p) {
-    constexpr int kStages = GemmCfg<GBN>::kStages;
-    constexpr int kBBytes = GemmCfg<GBN>::kBBytes;
+    using Cfg = GemmCfg<GBN, MT>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kABytes = Cfg::kABytes;
+    constexpr int kBBytes = Cfg::kBBytes;
+    constexpr int kAccStages = Cfg::kAccStages;
+    constexpr int TM = GBM * MT;   // tile rows
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -77,10 +91,10 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<kAccStages * GBN>(tmem_slot);
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -91,17 +105,20 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         int s = 0; uint32_t ph = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int tile = w % num_tiles, kb0 = (w / num_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
-            const int m0 = (tile % p.tiles_m) * GBM, n0 = (tile / p.tiles_m) * GBN;
+            const int m0 = (tile % p.tiles_m) * TM, n0 = (tile / p.tiles_m) * GBN;
+            const int mt_n = (MT == 2 && m0 + GBM < p.M) ? 2 : 1;   // 128-row sub-tiles that hold real rows
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], kABytes + kBBytes);
+                mbar_expect_tx(&full[s], mt_n * kASubBytes + kBBytes);
                 uint8_t* a = sA + s * kABytes;
                 uint8_t* b = sB + s * kBBytes;
-                if (!A_MN) {
-                    tma_load_2d(a, &tma_a, &full[s], kb * GBK, m0);
-                } else {
-                    tma_load_2d(a, &tma_a, &full[s], m0, kb * GBK);
-                    tma_load_2d(a + kABytes / 2, &tma_a, &full[s], m0 + 64, kb * GBK);
+                for (int mt = 0; mt < mt_n; ++mt) {
+                    if (!A_MN) {
+                        tma_load_2d(a + mt * kASubBytes, &tma_a, &full[s], kb * GBK, m0 + mt * GBM);
+                    } else {
+                        tma_load_2d(a + mt * kASubBytes, &tma_a, &full[s], m0 + mt * GBM, kb * GBK);
+                        tma_load_2d(a + mt * kASubBytes + kASubBytes / 2, &tma_a, &full[s], m0 + mt * GBM + 64, kb * GBK);
+                    }
                 }
                 if (!B_MN) {
                     tma_load_2d(b, &tma_b, &full[s], kb * GBK, n0);
@@ -122,9 +139,11 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int kb0 = (w / num_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+            const int m0 = ((w % num_tiles) % p.tiles_m) * TM;
+            const int mt_n = (MT == 2 && m0 + GBM < p.M) ? 2 : 1;
             mbar_wait(&acc_empty[as], aph ^ 1);
             tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + as * GBN;
+            const uint32_t d_tmem = tmem_base + as * MT * GBN;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[s], ph);
                 tcgen05_fence_after();
@@ -135,11 +154,14 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         // K-major, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart, +32 B per K=16 step.
                         // MN-major, 128B swizzle: 64-element column blocks (BK*128 B apart = LBO), 8 k-rows per
                         // 1024 B group (SBO), +16 k-rows = 2048 B per step.
-                        uint64_t da = A_MN ? make_smem_desc(a_addr + k * 2048, kABytes / 2, 1024, kSwizzle128B)
-                                           : make_smem_desc(a_addr + k * 32, 16, 1024, kSwizzle128B);
                         uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, GBK * 128, 1024, kSwizzle128B)
                                            : make_smem_desc(b_addr + k * 32, 16, 1024, kSwizzle128B);
-                        umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int mt = 0; mt < mt_n; ++mt) {   // the sub-tiles' MMAs share the B descriptor
+                            const uint32_t am = a_addr + mt * kASubBytes;
+                            uint64_t da = A_MN ? make_smem_desc(am + k * 2048, kASubBytes / 2, 1024, kSwizzle128B)
+                                               : make_smem_desc(am + k * 32, 16, 1024, kSwizzle128B);
+                            umma_f16(d_tmem + mt * GBN, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty[s]);
                     if (kb == kb1 - 1) umma_commit(&acc_full[as]);
@@ -152,56 +174,92 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             if (++as == kAccStages) { as = 0; aph ^= 1; }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        // tcgen05.ld hands thread i of the warp accumulator row 32q+i; a padded 32x32 shared-memory
-        // transpose turns that into row-contiguous 128-byte global stores (one row per instruction).
-        const int q = warp - 4;  // TMEM lanes [32q, 32q+32)
-        float* sw = sEpi + q * 32 * 33;
+        // ===================== epilogue: 8 warps =====================
+        // tcgen05.ld hands thread i of the warp accumulator row 32q+i; a padded 32x32 shared-memory transpose turns
+        // that into row-contiguous 128-byte global stores (one row per instruction).  Two warps share each TMEM lane
+        // quadrant and take alternate 32-column chunks; the load of a warp's next chunk is in flight while it stores
+        // the current one, and the accumulator is handed back to the MMA warp as soon as its last load has landed.
+        const int ew = warp - 4;
+        const int q = ew & 3, half = ew >> 2;   // TMEM lanes [32q, 32q+32); chunks half, half+2, ...
+        float* sw = sEpi + ew * 32 * 33;
         int as = 0; uint32_t aph = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int tile = w % num_tiles, split = w / num_tiles;
-            const int m0 = (tile % p.tiles_m) * GBM, n0 = (tile / p.tiles_m) * GBN;
+            const int mt_n = (MT == 2 && (tile % p.tiles_m) * TM + GBM < p.M) ? 2 : 1;
+            const int n0 = (tile / p.tiles_m) * GBN;
             const bool has_k = split * kb_per < num_kb;
-            mbar_wait(&acc_full[as], aph);
-            tcgen05_fence_after();
             const bool add_bias = p.bias != nullptr && split == 0;
+            const int nchunks = mt_n * (GBN / 32);
             float ss = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < GBN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * GBN + c * 32, v);
-                tmem_ld_wait();
+            auto load_chunk = [&](int cc, uint32_t (&v)[32]) {
+                const int mt = cc / (GBN / 32), c = cc % (GBN / 32);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (as * MT + mt) * GBN + c * 32, v);
+            };
+            auto release_acc = [&]() {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+            };
+            auto store_chunk = [&](int cc, const uint32_t (&v)[32]) {
+                const int mt = cc / (GBN / 32), c = cc % (GBN / 32);
+                const int m0 = (tile % p.tiles_m) * TM + mt * GBM;
                 const int nb = n0 + c * 32;
-                if (nb < p.N && m0 + q * 32 < p.M) {            // warp-uniform
+                if (nb >= p.N || m0 + q * 32 >= p.M) return;            // warp-uniform
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sw[lane * 33 + j] = has_k ? p.alpha * __uint_as_float(v[j]) : 0.f;
-                    __syncwarp();
-                    const int col = nb + lane;
-                    const float bv = (add_bias && col < p.N) ? p.bias[col] : 0.f;
-                    const int rows = min(32, p.M - (m0 + q * 32));
-                    if (col < p.N) {
-                        float* cptr = p.C + (int64_t)(m0 + q * 32) * p.ldc + col;
-                        if (p.splits > 1) {
-                            for (int r = 0; r < rows; ++r) atomicAdd(cptr + (int64_t)r * p.ldc, sw[r * 33 + lane] + bv);
-                        } else if (p.accumulate) {
-                            for (int r = 0; r < rows; ++r) cptr[(int64_t)r * p.ldc] += sw[r * 33 + lane] + bv;
+                for (int j = 0; j < 32; ++j) sw[lane * 33 + j] = has_k ? p.alpha * __uint_as_float(v[j]) : 0.f;
+                __syncwarp();
+                const int col = nb + lane;
+                const float bv = (add_bias && col < p.N) ? p.bias[col] : 0.f;
+                const int rows = min(32, p.M - (m0 + q * 32));
+                if (col < p.N) {
+                    float* cptr = p.C + (int64_t)(m0 + q * 32) * p.ldc + col;
+                    if (p.splits > 1) {
+                        if (rows == 32) {
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) atomicAdd(cptr + (int64_t)r * p.ldc, sw[r * 33 + lane] + bv);
                         } else {
-                            for (int r = 0; r < rows; ++r) {
-                                const float o = sw[r * 33 + lane] + bv;
-                                cptr[(int64_t)r * p.ldc] = o;
-                                ss += o * o;
-                            }
+                            for (int r = 0; r < rows; ++r) atomicAdd(cptr + (int64_t)r * p.ldc, sw[r * 33 + lane] + bv);
+                        }
+                    } else if (p.accumulate) {
+                        for (int r = 0; r < rows; ++r) cptr[(int64_t)r * p.ldc] += sw[r * 33 + lane] + bv;
+                    } else if (rows == 32) {
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const float o = sw[r * 33 + lane] + bv;
+                            cptr[(int64_t)r * p.ldc] = o;
+                            ss += o * o;
+                        }
+                    } else {
+                        for (int r = 0; r < rows; ++r) {
+                            const float o = sw[r * 33 + lane] + bv;
+                            cptr[(int64_t)r * p.ldc] = o;
+                            ss += o * o;
                         }
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
+            };
+            mbar_wait(&acc_full[as], aph);
+            tcgen05_fence_after();
+            uint32_t va[32], vb[32];
+            int cc = half;                       // nchunks >= 4: every warp owns at least two chunks
+            load_chunk(cc, va);
+            while (true) {
+                tmem_ld_wait();
+                const bool more_b = cc + 2 < nchunks;
+                if (more_b) load_chunk(cc + 2, vb); else release_acc();
+                store_chunk(cc, va);
+                if (!more_b) break;
+                tmem_ld_wait();
+                const bool more_a = cc + 4 < nchunks;
+                if (more_a) load_chunk(cc + 4, va); else release_acc();
+                store_chunk(cc + 2, vb);
+                if (!more_a) break;
+                cc += 4;
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
-            if (p.sumsq_out) {   // after the release of the accumulator: off the MMA warp's critical path
+            if (p.sumsq_out) {
                 ss = warp_sum(ss);
-                if (lane == 0) p.sumsq_out[tile * 4 + q] = ss;
+                if (lane == 0) p.sumsq_out[tile * 8 + ew] = ss;
             }
             if (++as == kAccStages) { as = 0; aph ^= 1; }
         }
@@ -209,7 +267,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    if (warp == 2) tmem_dealloc<kAccStages * GBN>(tmem_base);
+    if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -234,7 +292,7 @@ EncodeTiledFn get_encode() {
 }
 
 int g_num_sms = 0;
-bool g_attr_set[8] = {};
+bool g_attr_set[16] = {};
 
 }  // namespace
 
@@ -272,35 +330,63 @@ int tc_make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
     return ZRB_OK;
 }
 
-template <bool A_MN, bool B_MN, int GBN>
+template <bool A_MN, bool B_MN, int GBN, int MT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
-    auto kern = gemm_f16_tc_kernel<A_MN, B_MN, GBN>;
-    const int idx = (A_MN ? 2 : 0) + (B_MN ? 1 : 0) + (GBN == 256 ? 4 : 0);
+    auto kern = gemm_f16_tc_kernel<A_MN, B_MN, GBN, MT>;
+    const int idx = (A_MN ? 2 : 0) + (B_MN ? 1 : 0) + (GBN == 256 ? 4 : 0) + (MT == 2 ? 8 : 0);
     if (!g_attr_set[idx]) {
-        ZRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<GBN>::kSmem));
+        ZRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<GBN, MT>::kSmem));
         g_attr_set[idx] = true;
     }
     int grid = a.tiles_m * a.tiles_n * a.splits;
     if (grid > tc_num_sms()) grid = tc_num_sms();
-    kern<<<grid, kGemmThreads, GemmCfg<GBN>::kSmem, s>>>(ta, tb, a);
+    kern<<<grid, kGemmThreads, GemmCfg<GBN, MT>::kSmem, s>>>(ta, tb, a);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
 
-template <int GBN>
+template <int GBN, int MT>
 static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int a_mn, int b_mn,
                          cudaStream_t s) {
-    if (!a_mn && !b_mn) return launch_gemm<false, false, GBN>(ta, tb, a, s);
-    if (!a_mn && b_mn) return launch_gemm<false, true, GBN>(ta, tb, a, s);
-    if (a_mn && !b_mn) return launch_gemm<true, false, GBN>(ta, tb, a, s);
-    return launch_gemm<true, true, GBN>(ta, tb, a, s);
+    if (!a_mn && !b_mn) return launch_gemm<false, false, GBN, MT>(ta, tb, a, s);
+    if (!a_mn && b_mn) return launch_gemm<false, true, GBN, MT>(ta, tb, a, s);
+    if (a_mn && !b_mn) return launch_gemm<true, false, GBN, MT>(ta, tb, a, s);
+    return launch_gemm<true, true, GBN, MT>(ta, tb, a, s);
 }
 
-// number of sumsq_out slots gemm_f16_tc writes for an [M,N] output (same tile choice as below)
-int gemm_f16_tc_sumsq_slots(int M, int N) {
-    const int tiles_m = cdiv(M, GBM);
-    const int bn = (tiles_m * cdiv(N, 256) >= (tc_num_sms() * 9) / 10) ? 256 : 128;
-    return tiles_m * cdiv(N, bn) * 4;
+// Tile shape for an [M,N] output with K-block count num_kb: 128x256 when those tiles give every SM (nearly) a
+// full wave, else 128x128; few output tiles but a long contraction (the dgrads) split K in two.
+// ZRB_GEMM_MT=2 opts into 256x256 tiles (mt = 2, contraction split up to 8 ways when there are few tiles).  They
+// move a third fewer bytes per flop, but measured SLOWER on every shape of this path
+// (profiles/r01_gemm_tile_256x256_vs_128x256.json: e.g. [700x10000x1500] 37.2 vs 35.0 us, [6000x1500x700] 29.4 vs
+// 27.2 us, [700x6000x1500] 36.3 vs 22.7 us): each SM sustains only ~30 B/clk of 2-D TMA loads whatever the tile, so
+// what counts is how many SMs pull at once, and the single accumulator stage exposes the epilogue.
+struct TileChoice { int mt, bn, tiles_m, tiles_n, splits; };
+static TileChoice choose_tiles(int M, int N, int num_kb, bool can_split) {
+    static const bool mt2 = [] { const char* e = getenv("ZRB_GEMM_MT"); return e && e[0] == '2'; }();
+    const int nsm = tc_num_sms();
+    TileChoice c;
+    const int t2 = cdiv(M, 2 * GBM) * cdiv(N, 256);
+    int sp2 = 1;
+    if (can_split) while (sp2 < 8 && t2 * (sp2 * 2) <= nsm && num_kb / (sp2 * 2) >= 8) sp2 *= 2;
+    if (mt2 && M > GBM && t2 * sp2 >= (nsm * 45) / 100) {
+        c.mt = 2; c.bn = 256; c.tiles_m = cdiv(M, 2 * GBM); c.tiles_n = cdiv(N, 256); c.splits = sp2;
+        return c;
+    }
+    c.mt = 1;
+    c.tiles_m = cdiv(M, GBM);
+    c.bn = (c.tiles_m * cdiv(N, 256) >= (nsm * 9) / 10) ? 256 : 128;
+    c.tiles_n = cdiv(N, c.bn);
+    // few output tiles but a long contraction: split K in two so that ~all SMs work; partials added into a
+    // zeroed C with atomics
+    c.splits = (can_split && c.tiles_m * c.tiles_n * 2 <= nsm && num_kb >= 8) ? 2 : 1;
+    return c;
+}
+
+// number of sumsq_out slots gemm_f16_tc writes for an [M,N] output with contraction length K
+int gemm_f16_tc_sumsq_slots(int M, int N, int K) {
+    TileChoice c = choose_tiles(M, N, cdiv(K, GBK), false);
+    return c.tiles_m * c.tiles_n * kEpiWarps;
 }
 
 int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t ldb, int b_mn, float* C, int64_t ldc,
@@ -308,9 +394,8 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
     if (M <= 0 || N <= 0) return ZRB_OK;
     ZRB_REQUIRE(!sumsq_out || !accumulate, "sumsq_out needs a plain store epilogue");
     ZRB_REQUIRE(K > 0, "gemm_f16_tc needs K > 0");
-    // 128x256 tiles when they still give every SM (nearly) a full wave of work, else 128x128
-    const int tiles_m = cdiv(M, GBM);
-    const int bn = (tiles_m * cdiv(N, 256) >= (tc_num_sms() * 9) / 10) ? 256 : 128;
+    const TileChoice tc = choose_tiles(M, N, cdiv(K, GBK), !sumsq_out && ldc == N);
+    const int bn = tc.bn;
     CUtensorMap ta, tb;
     if (!a_mn) ZRB_TRY(tc_make_tmap_f16(&ta, A, K, M, lda, GBK, GBM, 1));
     else       ZRB_TRY(tc_make_tmap_f16(&ta, A, M, K, lda, 64, GBK, 1));
@@ -318,16 +403,14 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
     else       ZRB_TRY(tc_make_tmap_f16(&tb, B, N, K, ldb, 64, GBK, 1));
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.bias = bias; a.C = C; a.ldc = ldc; a.accumulate = accumulate;
-    a.tiles_m = tiles_m; a.tiles_n = cdiv(N, bn);
-    // few output tiles but a long contraction (the dgrads: 72 tiles x 94 K blocks): split K in two so
-    // that ~all SMs work; two partials added into a zeroed C are order-independent (a+b == b+a)
-    a.splits = 1;
+    a.tiles_m = tc.tiles_m; a.tiles_n = tc.tiles_n;
+    a.splits = tc.splits;
     a.sumsq_out = sumsq_out;
-    if (!sumsq_out && a.tiles_m * a.tiles_n * 2 <= tc_num_sms() && cdiv(K, GBK) >= 8 && ldc == N) {
-        a.splits = 2;
-        if (!accumulate) ZRB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));
-    }
-    return bn == 256 ? dispatch_gemm<256>(ta, tb, a, a_mn, b_mn, s) : dispatch_gemm<128>(ta, tb, a, a_mn, b_mn, s);
+    // split partials are added into a zeroed C: order-independent for two (a+b == b+a), last-bit run-to-run
+    // differences beyond that
+    if (a.splits > 1 && !accumulate) ZRB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));
+    if (tc.mt == 2) return dispatch_gemm<256, 2>(ta, tb, a, a_mn, b_mn, s);
+    return bn == 256 ? dispatch_gemm<256, 1>(ta, tb, a, a_mn, b_mn, s) : dispatch_gemm<128, 1>(ta, tb, a, a_mn, b_mn, s);
 }
 
 }  // namespace zrb
