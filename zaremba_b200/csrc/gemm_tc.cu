@@ -375,7 +375,14 @@ static TileChoice choose_tiles(int M, int N, int num_kb, bool can_split) {
     }
     c.mt = 1;
     c.tiles_m = cdiv(M, GBM);
-    c.bn = (c.tiles_m * cdiv(N, 256) >= (nsm * 9) / 10) ? 256 : 128;
+    const int t256 = c.tiles_m * cdiv(N, 256);
+    if (can_split && t256 * 4 <= nsm && t256 * 4 >= (nsm * 8) / 10 && num_kb / 4 >= 8) {
+        // the dgrads ([700 x 1500] outputs, 94..157 K blocks): 36 tiles of 128x256 with the contraction split in
+        // four move 25% fewer operand bytes per CTA than 72 tiles of 128x128 split in two
+        c.bn = 256; c.tiles_n = cdiv(N, 256); c.splits = 4;
+        return c;
+    }
+    c.bn = (t256 >= (nsm * 9) / 10) ? 256 : 128;
     c.tiles_n = cdiv(N, c.bn);
     // few output tiles but a long contraction: split K in two so that ~all SMs work; partials added into a
     // zeroed C with atomics

@@ -24,11 +24,10 @@ __device__ __forceinline__ float block_sum(float acc, float* sh) {
     return v;
 }
 
-// one run of `n` floats; partials[blockIdx.x] += sum of squares of this block's grid-stride share
-__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partials, int accumulate) {
-    __shared__ float sh[kThreads / 32];
+// sum of squares of this block's grid-stride share (blocks bx of nbx) of one run of `n` floats
+__device__ __forceinline__ float block_sumsq(const float* __restrict__ g, int64_t n, int bx, int nbx, float* sh) {
     float acc = 0.f;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)bx * blockDim.x + threadIdx.x, stride = (int64_t)nbx * blockDim.x;
     if ((((uintptr_t)g) & 15) == 0) {
         const float4* g4 = reinterpret_cast<const float4*>(g);
         const int64_t n4 = n >> 2;
@@ -49,8 +48,20 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* __re
     } else {
         for (int64_t j = tid; j < n; j += stride) acc += g[j] * g[j];
     }
-    float v = block_sum(acc, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = accumulate ? partials[blockIdx.x] + v : v;
+    return block_sum(acc, sh);
+}
+
+// runs of contiguous floats (the tensor list after merging neighbours); block (x, y) takes share x of run y and owns
+// partial slot y * gridDim.x + x, so one launch covers the whole list and no slot is written twice
+struct Runs {
+    float* p[16];
+    float* g[16];
+    int64_t n[16];
+};
+__global__ void sumsq_kernel(Runs r, float* __restrict__ partials) {
+    __shared__ float sh[kThreads / 32];
+    float v = block_sumsq(r.g[blockIdx.y], r.n[blockIdx.y], blockIdx.x, gridDim.x, sh);
+    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
 // scalars[0] = norm, scalars[1] = clip coefficient  (double accumulation of the partials)
@@ -76,8 +87,10 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partials, int n, 
 
 // g *= coef (clip_grad_norm_ scales .grad in place); p -= lr * g (main.py:117)
 template <bool WRITE_G>
-__global__ void clip_sgd_update_kernel(float* __restrict__ p, float* __restrict__ g, int64_t n, float lr,
-                                       const float* __restrict__ scalars) {
+__global__ void clip_sgd_update_kernel(Runs r, float lr, const float* __restrict__ scalars) {
+    float* __restrict__ p = r.p[blockIdx.y];
+    float* __restrict__ g = r.g[blockIdx.y];
+    const int64_t n = r.n[blockIdx.y];
     const float coef = scalars[1];
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     if (((((uintptr_t)g) | ((uintptr_t)p)) & 15) == 0) {
@@ -105,52 +118,60 @@ __global__ void clip_sgd_update_kernel(float* __restrict__ p, float* __restrict_
     }
 }
 
-// merge tensors that are adjacent in memory (both p and g) into runs
-static int coalesce(const TensorList& tl, float** p, float** g, int64_t* n) {
+// merge tensors that are adjacent in memory (both p and g) into runs; returns the run count and the block
+// count per run (sized for the longest run, all runs' partial slots fit in kNormBlocks)
+static int coalesce(const TensorList& tl, Runs* r, int* blocks_per_run) {
     int runs = 0;
+    int64_t longest = 0;
     for (int t = 0; t < tl.count; ++t) {
         if (tl.n[t] == 0) continue;
-        if (runs && p[runs - 1] + n[runs - 1] == tl.p[t] && g[runs - 1] + n[runs - 1] == tl.g[t]) {
-            n[runs - 1] += tl.n[t];
+        if (runs && r->p[runs - 1] + r->n[runs - 1] == tl.p[t] && r->g[runs - 1] + r->n[runs - 1] == tl.g[t]) {
+            r->n[runs - 1] += tl.n[t];
         } else {
-            p[runs] = tl.p[t]; g[runs] = tl.g[t]; n[runs] = tl.n[t];
+            r->p[runs] = tl.p[t]; r->g[runs] = tl.g[t]; r->n[runs] = tl.n[t];
             ++runs;
         }
     }
-    return runs;
-}
-
-static int blocks_for(int64_t n) {
-    int64_t b = (n / 4 + kThreads - 1) / kThreads;
+    for (int i = runs; i < 16; ++i) { r->p[i] = nullptr; r->g[i] = nullptr; r->n[i] = 0; }
+    for (int i = 0; i < runs; ++i) longest = r->n[i] > longest ? r->n[i] : longest;
+    int64_t b = (longest / 4 + kThreads - 1) / kThreads;
     if (b < 1) b = 1;
-    return (int)(b > kNormBlocks ? kNormBlocks : b);
+    const int cap = kNormBlocks / (runs > 0 ? runs : 1);
+    *blocks_per_run = (int)(b > cap ? cap : b);
+    return runs;
 }
 
 int norm_partials_base() { return kNormBlocks; }
 
 int grad_norm(const TensorList& tl, float max_norm, float* partials, float* scalars, float* norm_out,
               cudaStream_t s, bool extra_used, int n_gemm) {
-    float* p[16]; float* g[16]; int64_t n[16];
-    int runs = coalesce(tl, p, g, n);
+    Runs r;
+    int bpr = 1;
+    const int runs = coalesce(tl, &r, &bpr);
     ZRB_CUDA(cudaMemsetAsync(partials, 0, (kNormBlocks + (extra_used ? 0 : kNormExtra)) * sizeof(float), s));
-    for (int r = 0; r < runs; ++r) {
-        sumsq_kernel<<<blocks_for(n[r]), kThreads, 0, s>>>(g[r], n[r], partials, 1);
+    if (runs) {
+        sumsq_kernel<<<dim3(bpr, runs), kThreads, 0, s>>>(r, partials);
         ZRB_KERNEL_CHECK();
     }
-    norm_finalize_kernel<<<1, 256, 0, s>>>(partials, kNormBlocks + kNormExtra + n_gemm, max_norm, scalars, norm_out);
+    // one block, 1024 threads: up to ~15k partials, a handful of independent loads per thread
+    norm_finalize_kernel<<<1, 1024, 0, s>>>(partials, kNormBlocks + kNormExtra + n_gemm, max_norm, scalars, norm_out);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
 
 // update only (norm / coefficient already in `scalars`)
 int sgd_apply(const TensorList& tl, float lr, const float* scalars, bool write_g, cudaStream_t s) {
-    float* p[16]; float* g[16]; int64_t n[16];
-    int runs = coalesce(tl, p, g, n);
-    for (int r = 0; r < runs; ++r) {
-        if (write_g) clip_sgd_update_kernel<true><<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
-        else clip_sgd_update_kernel<false><<<blocks_for(n[r]) * 2, kThreads, 0, s>>>(p[r], g[r], n[r], lr, scalars);
-        ZRB_KERNEL_CHECK();
-    }
+    Runs r;
+    int bpr = 1;
+    const int runs = coalesce(tl, &r, &bpr);
+    if (!runs) return ZRB_OK;
+    int64_t longest = 0;   // grid.x sized for the longest run (no slot limit here); shorter runs leave blocks idle
+    for (int i = 0; i < runs; ++i) longest = r.n[i] > longest ? r.n[i] : longest;
+    int64_t b = (longest / 4 + kThreads - 1) / kThreads;
+    const int bx = (int)(b < 1 ? 1 : (b > kNormBlocks ? kNormBlocks : b)) * 2;
+    if (write_g) clip_sgd_update_kernel<true><<<dim3(bx, runs), kThreads, 0, s>>>(r, lr, scalars);
+    else clip_sgd_update_kernel<false><<<dim3(bx, runs), kThreads, 0, s>>>(r, lr, scalars);
+    ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
 
