@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_parity.py > gpurun_out/dp_parity.log 2>&1; echo "parity rc=$?"; grep -v "^\*\|OMP" gpurun_out/dp_parity.log | tail -12
 for tr in ce nccl; do
-ZRB_DP_TRANSPORT=$tr timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_dp2_$tr.json 2> gpurun_out/bench_dp2_$tr.err; echo "bench $tr rc=$?"
+ZRB_DP_TRANSPORT=$tr timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 60 --warmup 10 --no-cpu-baseline > gpurun_out/bench_dp2_$tr.json 2> gpurun_out/bench_dp2_$tr.err; echo "bench $tr rc=$?"
 python - <<PY
 import json
 for line in open('gpurun_out/bench_dp2_$tr.json'):

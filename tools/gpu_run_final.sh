@@ -11,5 +11,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:
 for k in lstm_rec_fwd_kernel gemm_f16_tc_kernel softmax_nll_kernel update_pack; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 3 -f -o gpurun_out/prof_$k python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?"
 done
+ZRB_NO_COOP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_bwd_kernel -s 2 -c 2 -f -o gpurun_out/prof_lstm_rec_bwd_kernel python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_lstm_rec_bwd_kernel.log 2>&1; echo "ncu rec_bwd rc=$?"
 timeout 120 python tools/rec_trace.py large > gpurun_out/rec_trace_large.json 2>/dev/null
 ls -la gpurun_out/*.ncu-rep | wc -l

@@ -69,7 +69,16 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partials, int n, 
                                      float* __restrict__ scalars, float* __restrict__ norm_out) {
     __shared__ double sh[32];
     double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partials[i];
+    // up to ~15k partials: batches of 8 independent loads per thread (a rolled loop pays one L2 round trip per load)
+    int i = threadIdx.x;
+    for (; i + 7 * (int)blockDim.x < n; i += 8 * (int)blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = partials[i + k * (int)blockDim.x];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += (double)v[k];
+    }
+    for (; i < n; i += blockDim.x) acc += (double)partials[i];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
