@@ -262,6 +262,94 @@ __global__ void softmax_nll_kernel(const float* __restrict__ scores, const int64
     }
 }
 
+// Same function with the row held in registers: one block per token, every thread loads NV float4 chunks ONCE
+// (the scalar kernel above reads the row twice and carries the online-softmax recurrence through every element),
+// block max, one exp per element, block sum, then the gradient is written from the registers with 16-byte
+// (fp32) / 8-byte (fp16 image) stores.  Needs V % 4 == 0, V <= 4 * 512 * NV and 16-byte aligned rows.
+constexpr int kSmThreads = 512;
+__device__ __forceinline__ float block_reduce_512(float v, float* sh, bool is_max) {
+    for (int o = 16; o > 0; o >>= 1) {
+        float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, t) : v + t;
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();                       // sh may still be read from the previous reduction
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    v = l < kSmThreads / 32 ? sh[l] : (is_max ? -INFINITY : 0.f);
+    for (int o = 16; o > 0; o >>= 1) {
+        float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, t) : v + t;
+    }
+    return v;                              // every thread holds the block result (fixed tree: deterministic)
+}
+template <int NV>
+__global__ void __launch_bounds__(kSmThreads) softmax_nll_reg_kernel(
+    const float* __restrict__ scores, const int64_t* __restrict__ y, int N, int V, float gscale,
+    float* __restrict__ row_loss, float* __restrict__ dscores, float* __restrict__ tgt_prob, __half* __restrict__ ds_h,
+    int64_t ld_s, float h_scale) {
+    __shared__ float sh[32];
+    const int n = blockIdx.x;
+    const float* row = scores + (int64_t)n * V;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int nv4 = V >> 2;
+    float4 z[NV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = threadIdx.x + k * kSmThreads;
+        if (i < nv4) {
+            z[k] = __ldcs(row4 + i);
+            mx = fmaxf(mx, fmaxf(fmaxf(z[k].x, z[k].y), fmaxf(z[k].z, z[k].w)));
+        }
+    }
+    mx = block_reduce_512(mx, sh, true);
+    if (mx == -INFINITY) mx = 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = threadIdx.x + k * kSmThreads;
+        if (i < nv4) {
+            z[k].x = __expf(z[k].x - mx); z[k].y = __expf(z[k].y - mx);
+            z[k].z = __expf(z[k].z - mx); z[k].w = __expf(z[k].w - mx);
+            sum += (z[k].x + z[k].y) + (z[k].z + z[k].w);
+        }
+    }
+    sum = block_reduce_512(sum, sh, false);
+    const float inv = 1.f / sum;
+    const int64_t tgt = y[n];
+    if (threadIdx.x == 0) {
+        const float zt = (tgt >= 0 && tgt < V) ? row[tgt] : mx;
+        row_loss[n] = -(zt - mx - logf(sum));
+        if (tgt_prob) tgt_prob[n] = expf(zt - mx) * inv;
+    }
+    if (dscores || ds_h) {
+        float4* drow = dscores ? reinterpret_cast<float4*>(dscores + (int64_t)n * V) : nullptr;
+        uint2* hrow = ds_h ? reinterpret_cast<uint2*>(ds_h + (int64_t)n * ld_s) : nullptr;
+        const float g = gscale * inv;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int i = threadIdx.x + k * kSmThreads;
+            if (i < nv4) {
+                float4 p = make_float4(z[k].x * g, z[k].y * g, z[k].z * g, z[k].w * g);
+                const int64_t d = tgt - 4 * (int64_t)i;        // the target's position inside this chunk, if any
+                if (d == 0) p.x -= gscale; else if (d == 1) p.y -= gscale; else if (d == 2) p.z -= gscale;
+                else if (d == 3) p.w -= gscale;
+                if (drow) drow[i] = p;
+                if (hrow) {
+                    const float lo = -65504.f, hi = 65504.f;
+                    __half2 a = __floats2half2_rn(fminf(fmaxf(p.x * h_scale, lo), hi), fminf(fmaxf(p.y * h_scale, lo), hi));
+                    __half2 b = __floats2half2_rn(fminf(fmaxf(p.z * h_scale, lo), hi), fminf(fmaxf(p.w * h_scale, lo), hi));
+                    uint2 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&a);
+                    u.y = *reinterpret_cast<uint32_t*>(&b);
+                    hrow[i] = u;
+                }
+            }
+        }
+    }
+}
+
 // loss = (B / N) * sum_n row_loss[n]  (fixed-order tree: deterministic)
 __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int N, float scale, float* __restrict__ loss) {
     __shared__ float sh[32];
@@ -281,7 +369,18 @@ int softmax_nll(const float* scores, const int64_t* y, int N, int V, int B, floa
                 float* dscores, float* tgt_prob, cudaStream_t s, __half* ds_h, int64_t ld_s, float h_scale) {
     if (N == 0) return ZRB_OK;
     float gscale = (float)((double)B / (double)N);
-    softmax_nll_kernel<<<N, 512, 0, s>>>(scores, y, N, V, gscale, row_loss, dscores, tgt_prob, ds_h, ld_s, h_scale);
+    const bool vec = V % 4 == 0 && V <= 4 * kSmThreads * 8 && (((uintptr_t)scores) & 15) == 0 &&
+                     (!dscores || (((uintptr_t)dscores) & 15) == 0) &&
+                     (!ds_h || ((((uintptr_t)ds_h) & 7) == 0 && ld_s % 4 == 0));
+    const int nv = vec ? (V / 4 + kSmThreads - 1) / kSmThreads : 0;
+#define ZRB_SM_LAUNCH(NV) \
+    softmax_nll_reg_kernel<NV><<<N, kSmThreads, 0, s>>>(scores, y, N, V, gscale, row_loss, dscores, tgt_prob, ds_h, ld_s, h_scale)
+    if (vec && nv <= 2) ZRB_SM_LAUNCH(2);
+    else if (vec && nv <= 4) ZRB_SM_LAUNCH(4);
+    else if (vec && nv <= 6) ZRB_SM_LAUNCH(6);
+    else if (vec) ZRB_SM_LAUNCH(8);
+    else softmax_nll_kernel<<<N, 512, 0, s>>>(scores, y, N, V, gscale, row_loss, dscores, tgt_prob, ds_h, ld_s, h_scale);
+#undef ZRB_SM_LAUNCH
     ZRB_KERNEL_CHECK();
     if (loss) {
         loss_reduce_kernel<<<1, 256, 0, s>>>(row_loss, N, gscale, loss);
