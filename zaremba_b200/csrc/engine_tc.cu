@@ -19,7 +19,6 @@ struct zrb_tc_state {
     __half* w_ih_h[ZRB_MAX_LAYERS] = {};
     __half* w_hh_h[ZRB_MAX_LAYERS] = {};
     __half* fc_w_h = nullptr;
-    float* bsum[ZRB_MAX_LAYERS] = {};
     __half* x_h[ZRB_MAX_LAYERS + 1] = {};
     __half* hprev_h[ZRB_MAX_LAYERS] = {};
     __half* dG_h = nullptr;
@@ -30,8 +29,10 @@ struct zrb_tc_state {
     // persistent recurrence
     zrb::RecPlan fplan{};
     __half* w_img_f[ZRB_MAX_LAYERS] = {};
+    __half* h0_img[ZRB_MAX_LAYERS] = {};   // image of the state entering the window (step 0's B operand)
     __half* h_img = nullptr;
-    unsigned int* counter = nullptr;
+    unsigned int* counter = nullptr;       // [0]: forward grid barrier, [32]: backward; never reset between launches,
+    unsigned int cnt_f = 0, cnt_b = 0;     // their values when the next launch starts
     zrb::RecPlan bplan{};
     __half* w_img_b[ZRB_MAX_LAYERS] = {};
     __half* g_img = nullptr;
@@ -79,7 +80,6 @@ int tc_ctx_init(zrb_ctx* c) {
     for (int l = 0; l < L; ++l) {
         ZRB_TRY(tc_alloc(c, &t->w_ih_h[l], (size_t)4 * H * t->Hp));
         ZRB_TRY(tc_alloc(c, &t->w_hh_h[l], (size_t)4 * H * t->Hp));
-        ZRB_TRY(tc_alloc(c, &t->bsum[l], (size_t)4 * H));
         ZRB_TRY(tc_alloc(c, &t->hprev_h[l], (N + B) * t->Hp));
     }
     for (int l = 0; l <= L; ++l) ZRB_TRY(tc_alloc(c, &t->x_h[l], N * t->Hp));
@@ -91,7 +91,10 @@ int tc_ctx_init(zrb_ctx* c) {
     if (force && !strcmp(force, "steps")) t->fplan.ok = 0;   // A/B switch: per-timestep launches
     if (t->fplan.ok) {
         const RecPlan& fp = t->fplan;
-        for (int l = 0; l < L; ++l) ZRB_TRY(tc_alloc(c, &t->w_img_f[l], (size_t)fp.nCTA * fp.Kc * fp.G * 64));
+        for (int l = 0; l < L; ++l) {
+            ZRB_TRY(tc_alloc(c, &t->w_img_f[l], (size_t)fp.nCTA * fp.Kc * fp.G * 64));
+            ZRB_TRY(tc_alloc(c, &t->h0_img[l], (size_t)fp.Kc * fp.GB * 64));
+        }
         ZRB_TRY(tc_alloc(c, &t->h_img, (size_t)(c->cfg.max_seq + 1) * fp.Kc * fp.GB * 64));
         ZRB_TRY(tc_alloc(c, &t->counter, 64));
     }
@@ -122,7 +125,6 @@ static int tc_pack_weights(zrb_ctx* c, const zrb_params* p, cudaStream_t s) {
     for (int l = 0; l < L; ++l) {
         ZRB_TRY(convert_pad_f16(p->w_ih[l], H, t->w_ih_h[l], t->Hp, 4 * H, H, 1.f, s));
         ZRB_TRY(convert_pad_f16(p->w_hh[l], H, t->w_hh_h[l], t->Hp, 4 * H, H, 1.f, s));
-        ZRB_TRY(add_vec(p->b_ih[l], p->b_hh[l], t->bsum[l], 4 * H, s));
         if (t->fplan.ok) ZRB_TRY(pack_whh_fwd(p->w_hh[l], t->w_img_f[l], H, t->fplan, s));
         if (t->bplan.ok) ZRB_TRY(pack_whh_bwd(p->w_hh[l], t->w_img_b[l], H, t->bplan, s));
     }
@@ -139,11 +141,15 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
     const int Hp = t->Hp;
     const size_t bh = (size_t)B * H * sizeof(float);
     ZRB_TRY(tc_pack_weights(c, p, s));
-    ZRB_CUDA(cudaMemcpyAsync(c->x_saved, x, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    for (int l = 0; l < L; ++l) {
-        ZRB_CUDA(cudaMemcpyAsync(c->h0s[l], in->h[l], bh, cudaMemcpyDeviceToDevice, s));
-        ZRB_CUDA(cudaMemcpyAsync(c->c0s[l], in->c[l], bh, cudaMemcpyDeviceToDevice, s));
-        ZRB_TRY(convert_pad_f16(c->h0s[l], H, t->hprev_h[l], Hp, B, H, 1.f, s));
+    {   // state copies (in / out may be the same buffers), fp16 h0 rows and images, saved tokens: one launch
+        FwdPrep fp = {};
+        for (int l = 0; l < L; ++l) {
+            fp.in_h[l] = in->h[l]; fp.in_c[l] = in->c[l]; fp.h0s[l] = c->h0s[l]; fp.c0s[l] = c->c0s[l];
+            fp.hprev_h[l] = t->hprev_h[l]; fp.h0_img[l] = t->fplan.ok ? t->h0_img[l] : nullptr;
+        }
+        fp.x = x; fp.x_saved = c->x_saved;
+        fp.L = L; fp.B = B; fp.H = H; fp.Hp = Hp; fp.GB = t->fplan.GB; fp.Kc = t->fplan.Kc; fp.N = N;
+        ZRB_TRY(fwd_prep(fp, s));
     }
     {
         ProfScope ps(c, ZRB_PROF_EMBED_FWD, s);
@@ -153,14 +159,21 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
         float* G = c->gates[l];
         {
             ProfScope ps(c, ZRB_PROF_GEMM_IN, s);
-            ZRB_TRY(gemm_f16_tc(t->x_h[l], Hp, 0, t->w_ih_h[l], Hp, 0, G, 4 * H, N, 4 * H, H, 1.f, t->bsum[l], 0, s));
+            ZRB_TRY(gemm_f16_tc(t->x_h[l], Hp, 0, t->w_ih_h[l], Hp, 0, G, 4 * H, N, 4 * H, H, 1.f, p->b_ih[l], 0, s, nullptr,
+                                p->b_hh[l]));
         }
         MaskSrc m = site_mask(c, l + 1);
         ProfScope ps(c, ZRB_PROF_REC_FWD, s);
         if (t->fplan.ok) {
-            ZRB_TRY(pack_h_image(c->h0s[l], t->h_img, B, H, t->fplan, s));
-            ZRB_TRY(lstm_rec_fwd(t->fplan, t->w_img_f[l], t->h_img, G, c->c0s[l], c->cst[l], out->h[l], out->c[l],
-                                 t->hprev_h[l], t->x_h[l + 1], t->counter, T, B, H, Hp, m, s, t->trace));
+            const unsigned int arrivals = (unsigned int)T * (unsigned int)t->fplan.nCTA;
+            if (t->cnt_f > 0xF0000000u - arrivals) {   // far from wrapping: once per ~900k launches
+                ZRB_CUDA(cudaMemsetAsync(t->counter, 0, sizeof(unsigned int), s));
+                t->cnt_f = 0;
+            }
+            ZRB_TRY(lstm_rec_fwd(t->fplan, t->w_img_f[l], t->h0_img[l], t->h_img, G, c->c0s[l], c->cst[l], out->h[l],
+                                 out->c[l], t->hprev_h[l], t->x_h[l + 1], t->counter, t->cnt_f, T, B, H, Hp, m, s,
+                                 t->trace));
+            t->cnt_f += arrivals;
             continue;
         }
         for (int tt = 0; tt < T; ++tt) {
@@ -237,13 +250,20 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
     float* dX = c->bwd_dx;
     {
         MaskSrc m = site_mask(c, l + 1);
-        ZRB_CUDA(cudaMemsetAsync(c->dc, 0, bh * sizeof(float), s));
         if (t->bplan.ok) {
             ProfScope ps(c, ZRB_PROF_REC_BWD, s);
+            const unsigned int arrivals = (unsigned int)T * (unsigned int)t->bplan.nCTA;
+            if (t->cnt_b > 0xF0000000u - arrivals) {
+                ZRB_CUDA(cudaMemsetAsync(t->counter + 32, 0, sizeof(unsigned int), s));
+                t->cnt_b = 0;
+            }
             ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], t->dG_h,
-                                 t->counter, T, B, H, G4p, m, s, t->trace ? t->trace + (size_t)c->cfg.max_seq * 8 : nullptr));
+                                 t->counter + 32, t->cnt_b, T, B, H, G4p, m, s,
+                                 t->trace ? t->trace + (size_t)c->cfg.max_seq * 8 : nullptr));
+            t->cnt_b += arrivals;
         } else {
             ProfScope ps(c, ZRB_PROF_REC_BWD, s);
+            ZRB_CUDA(cudaMemsetAsync(c->dc, 0, bh * sizeof(float), s));   // (the persistent kernel keeps dc in registers)
             for (int tt = T - 1; tt >= 0; --tt) {
                 const float* c_prev = tt ? c->cst[l] + (size_t)(tt - 1) * bh : c->c0s[l];
                 ZRB_TRY(lstm_cell_bwd_tc(dY + (size_t)tt * bh, tt == T - 1 ? nullptr : c->dh_rec, c->dc,
@@ -399,7 +419,6 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
                         c->keep_clipped, s));
     push(f + 1);
     ZRB_TRY(sgd_apply(rest, lr, c->scalars, c->keep_clipped, s));
-    for (int l = 0; l < L; ++l) ZRB_TRY(add_vec(p->b_ih[l], p->b_hh[l], t->bsum[l], 4 * H, s));
     t->wg_ok = false;
     c->weights_version++;
     t->packed_version = c->weights_version;      // images are current

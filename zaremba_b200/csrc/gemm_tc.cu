@@ -50,6 +50,7 @@ struct GemmArgs {
     int M, N, K;
     float alpha;
     const float* bias;
+    const float* bias2;   // or null: a second bias vector added with the first (b_ih + b_hh, model.py:35)
     float* C;
     int64_t ldc;
     int accumulate;
@@ -209,7 +210,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 for (int j = 0; j < 32; ++j) sw[lane * 33 + j] = has_k ? p.alpha * __uint_as_float(v[j]) : 0.f;
                 __syncwarp();
                 const int col = nb + lane;
-                const float bv = (add_bias && col < p.N) ? p.bias[col] : 0.f;
+                const float bv = (add_bias && col < p.N) ? p.bias[col] + (p.bias2 ? p.bias2[col] : 0.f) : 0.f;
                 const int rows = min(32, p.M - (m0 + q * 32));
                 if (col < p.N) {
                     float* cptr = p.C + (int64_t)(m0 + q * 32) * p.ldc + col;
@@ -397,8 +398,10 @@ int gemm_f16_tc_sumsq_slots(int M, int N, int K) {
 }
 
 int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t ldb, int b_mn, float* C, int64_t ldc,
-                int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, float* sumsq_out) {
+                int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, float* sumsq_out,
+                const float* bias2) {
     if (M <= 0 || N <= 0) return ZRB_OK;
+    ZRB_REQUIRE(!bias2 || bias, "bias2 needs bias");
     ZRB_REQUIRE(!sumsq_out || !accumulate, "sumsq_out needs a plain store epilogue");
     ZRB_REQUIRE(K > 0, "gemm_f16_tc needs K > 0");
     const TileChoice tc = choose_tiles(M, N, cdiv(K, GBK), !sumsq_out && ldc == N);
@@ -413,6 +416,7 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
     a.tiles_m = tc.tiles_m; a.tiles_n = tc.tiles_n;
     a.splits = tc.splits;
     a.sumsq_out = sumsq_out;
+    a.bias2 = bias2;
     // split partials are added into a zeroed C: order-independent for two (a+b == b+a), last-bit run-to-run
     // differences beyond that
     if (a.splits > 1 && !accumulate) ZRB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));
@@ -427,5 +431,5 @@ extern "C" int zrb_gemm_f16(const void* A, int64_t lda, int32_t a_mn_major, cons
                             const float* bias, int32_t accumulate, void* stream) {
     ZRB_REQUIRE(A && B && C, "null argument");
     return zrb::gemm_f16_tc((const __half*)A, lda, a_mn_major, (const __half*)B, ldb, b_mn_major, C, ldc, M, N, K,
-                            alpha, bias, accumulate, (cudaStream_t)stream, nullptr);
+                            alpha, bias, accumulate, (cudaStream_t)stream, nullptr, nullptr);
 }

@@ -30,7 +30,8 @@ struct RecBwdArgs {
     const float* cst;         // [N,H]
     const float* c0;          // [B,H]
     __half* dG_h;             // [N,G4p] row-major, kGradScale * dG
-    unsigned int* counter;
+    unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
+    unsigned int base;
     int T, B, H, G4p, U, G, GB, Kc, nCTA;
     MaskSrc m;
     long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         const int lbo_b = a.GB * 128;
         for (int s = 1; s < T; ++s) {
             const int t = T - 1 - s;                      // step being computed; needs dG_{t+1}
-            grid_counter_wait(a.counter, (unsigned int)s * a.nCTA);
+            grid_counter_wait(a.counter, a.base + (unsigned int)s * a.nCTA);
             if (tr) a.trace[s * 8 + 0] = clock64();
             fence_proxy_async_global();
             const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + rank) * b_bytes;
@@ -364,15 +365,15 @@ int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
 }
 
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
-                 const float* cst, const float* c0, __half* dG_h, unsigned int* counter, int T, int B, int H, int G4p,
-                 MaskSrc m, cudaStream_t s, long long* trace) {
+                 const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
+                 int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace) {
     static bool attr = false;
     if (!attr) {
         ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    ZRB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
     RecBwdArgs a;
+    a.base = counter_base;
     a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
     a.counter = counter;
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;

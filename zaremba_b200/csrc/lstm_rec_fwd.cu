@@ -31,7 +31,8 @@ namespace zrb {
 
 struct RecFwdArgs {
     const __half* w_img;      // [nCTA][Kc][G][8][8]
-    __half* h_img;            // [T+1][Kc][GB][8][8]; image t is the B operand of step t
+    const __half* h0_img;     // [Kc][GB][8][8] image of the state entering the window: the B operand of step 0
+    __half* h_img;            // [T+1][Kc][GB][8][8]; image t (t >= 1) is the B operand of step t, written by step t-1
     float* gates;             // [N,4H] in: x-part pre-activations (+biases); out: activated gates
     const float* c0;          // [B,H]
     float* cst;               // [N,H]
@@ -39,7 +40,8 @@ struct RecFwdArgs {
     float* c_last;            // [B,H] or null
     __half* hprev_h;          // [N+B,Hp] row-major, rows B.. written here
     __half* y_h;              // [N,Hp] row-major dropout(h)
-    unsigned int* counter;    // grid barrier, zeroed before launch
+    unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
+    unsigned int base;
     int T, B, H, Hp, U, G, GB, Kc, nCTA;
     MaskSrc m;
     long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
@@ -89,10 +91,10 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
         const int lbo_b = a.GB * 128;
         for (int t = 0; t < a.T; ++t) {
-            if (t > 0) grid_counter_wait(a.counter, (unsigned int)t * a.nCTA);
+            if (t > 0) grid_counter_wait(a.counter, a.base + (unsigned int)t * a.nCTA);
             if (tr) a.trace[t * 8 + 0] = clock64();
             fence_proxy_async_global();
-            const uint8_t* img = (const uint8_t*)a.h_img + (size_t)t * b_bytes;
+            const uint8_t* img = t == 0 ? (const uint8_t*)a.h0_img : (const uint8_t*)a.h_img + (size_t)t * b_bytes;
             for (int pc = 0; pc < kRecPieces; ++pc) {
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
                 if (k0 >= k1) { mbar_arrive(&bar_b[pc]); continue; }
@@ -260,17 +262,6 @@ __global__ void pack_whh_fwd_kernel(const float* __restrict__ W, __half* __restr
     }
 }
 
-// image[kc][g][r][e] = half(h[b = g*8+r, k = kc*8+e])
-__global__ void pack_h_image_kernel(const float* __restrict__ h, __half* __restrict__ img, int B, int H, int GB,
-                                    int Kc) {
-    const int total = Kc * GB * 64;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        int e = idx & 7, r = (idx >> 3) & 7, g = (idx >> 6) % GB, kc = (idx >> 6) / GB;
-        int b = g * 8 + r, k = kc * 8 + e;
-        img[idx] = __float2half_rn((b < B && k < H) ? h[(size_t)b * H + k] : 0.f);
-    }
-}
-
 // ---- host ------------------------------------------------------------------------------------------
 size_t rec_smem_bytes(int Kc, int G, int GB) {
     return (size_t)Kc * G * 128 + (size_t)Kc * GB * 128 + 2 * 64 * (GB * 8 + 1) * 4 + 128 /*align*/ + 128 /*bars*/;
@@ -304,23 +295,17 @@ int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
     return ZRB_OK;
 }
 
-int pack_h_image(const float* h, __half* img, int B, int H, const RecPlan& p, cudaStream_t s) {
-    pack_h_image_kernel<<<cdiv(p.Kc * p.GB * 64, 256), 256, 0, s>>>(h, img, B, H, p.GB, p.Kc);
-    ZRB_KERNEL_CHECK();
-    return ZRB_OK;
-}
-
-int lstm_rec_fwd(const RecPlan& p, const __half* w_img, __half* h_img, float* gates, const float* c0, float* cst,
-                 float* h_last, float* c_last, __half* hprev_h, __half* y_h, unsigned int* counter, int T, int B, int H,
-                 int Hp, MaskSrc m, cudaStream_t s, long long* trace) {
+int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
+                 const float* c0, float* cst, float* h_last, float* c_last, __half* hprev_h, __half* y_h,
+                 unsigned int* counter, unsigned int counter_base, int T, int B, int H, int Hp, MaskSrc m, cudaStream_t s,
+                 long long* trace) {
     static bool attr = false;
     if (!attr) {
         ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    ZRB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
     RecFwdArgs a;
-    a.w_img = w_img; a.h_img = h_img; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;
+    a.w_img = w_img; a.h0_img = h0_img; a.h_img = h_img; a.base = counter_base; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;
     a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter;
     a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
     a.trace = trace;

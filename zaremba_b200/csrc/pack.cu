@@ -28,12 +28,36 @@ int convert_pad_f16(const float* src, int64_t ld_src, __half* dst, int64_t ld_ds
     return ZRB_OK;
 }
 
-__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = a[i] + b[i];
+__global__ void fwd_prep_kernel(FwdPrep a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int bh = a.B * a.H, bhp = a.B * a.Hp, img_n = a.Kc * a.GB * 64;
+    for (int l = 0; l < a.L; ++l) {
+        const float* __restrict__ h = a.in_h[l];
+        const float* __restrict__ c = a.in_c[l];
+        for (int i = tid; i < bh; i += nth) {
+            a.h0s[l][i] = h[i];
+            a.c0s[l][i] = c[i];
+        }
+        for (int i = tid; i < bhp; i += nth) {
+            const int r = i / a.Hp, col = i % a.Hp;
+            a.hprev_h[l][i] = __float2half_rn(col < a.H ? h[(size_t)r * a.H + col] : 0.f);
+        }
+        if (a.h0_img[l]) {
+            for (int i = tid; i < img_n; i += nth) {
+                const int e = i & 7, r = (i >> 3) & 7, g = (i >> 6) % a.GB, kc = (i >> 6) / a.GB;
+                const int b = g * 8 + r, k = kc * 8 + e;
+                a.h0_img[l][i] = __float2half_rn((b < a.B && k < a.H) ? h[(size_t)b * a.H + k] : 0.f);
+            }
+        }
+    }
+    for (int i = tid; i < a.N; i += nth) a.x_saved[i] = a.x[i];
 }
-int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s) {
-    add_vec_kernel<<<cdiv(n, 256), 256, 0, s>>>(a, b, out, n);
+int fwd_prep(const FwdPrep& a, cudaStream_t s) {
+    const int work = max(max(a.B * a.Hp, a.Kc * a.GB * 64), a.N);
+    int blocks = cdiv(work, 256);
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks < 1) blocks = 1;
+    fwd_prep_kernel<<<blocks, 256, 0, s>>>(a);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }

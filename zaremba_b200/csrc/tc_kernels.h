@@ -9,7 +9,6 @@ constexpr float kGradScale = 1024.f;   // fp16 gradient images hold kGradScale *
 
 int convert_pad_f16(const float* src, int64_t ld_src, __half* dst, int64_t ld_dst, int rows, int cols, float scale,
                     cudaStream_t s);
-int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
 int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, cudaStream_t s);
 
 // cell pointwise with fp16 side outputs (tc_cell.cu)
@@ -32,17 +31,36 @@ struct RecPlan {
 size_t rec_smem_bytes(int Kc, int G, int GB);
 int rec_fwd_plan(int H, int B, RecPlan* plan);
 int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s);
-int pack_h_image(const float* h, __half* img, int B, int H, const RecPlan& p, cudaStream_t s);
-int lstm_rec_fwd(const RecPlan& p, const __half* w_img, __half* h_img, float* gates, const float* c0, float* cst,
-                 float* h_last, float* c_last, __half* hprev_h, __half* y_h, unsigned int* counter, int T, int B, int H,
-                 int Hp, MaskSrc m, cudaStream_t s, long long* trace = nullptr);
+// h0_img: the B operand of step 0 (image of the state entering the window, built by fwd_prep); h_img slot t+1 is
+// written by step t.  The grid-barrier counter is never reset between launches: `counter_base` is its value when
+// the launch starts (the caller adds T * nCTA per launch).
+int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
+                 const float* c0, float* cst, float* h_last, float* c_last, __half* hprev_h, __half* y_h,
+                 unsigned int* counter, unsigned int counter_base, int T, int B, int H, int Hp, MaskSrc m, cudaStream_t s,
+                 long long* trace = nullptr);
+// Everything the forward needs from the incoming state and tokens in ONE launch (it replaced 9: five device
+// copies, two fp16 conversions, two image packs): h0s/c0s = copies of the incoming (h, c) (the caller may pass
+// the same buffers for the outgoing state), hprev_h rows [0,B) = half(h0) with zeroed pad columns, h0_img = the
+// UMMA-layout image [kc][g][r][e] = half(h0[b = g*8+r, k = kc*8+e]) (null: not built), x_saved = x.
+struct FwdPrep {
+    const float* in_h[ZRB_MAX_LAYERS];
+    const float* in_c[ZRB_MAX_LAYERS];
+    float* h0s[ZRB_MAX_LAYERS];
+    float* c0s[ZRB_MAX_LAYERS];
+    __half* hprev_h[ZRB_MAX_LAYERS];
+    __half* h0_img[ZRB_MAX_LAYERS];
+    const int64_t* x;
+    int64_t* x_saved;
+    int L, B, H, Hp, GB, Kc, N;
+};
+int fwd_prep(const FwdPrep& a, cudaStream_t s);
 // SGD update of one matrix fused with its fp16 image rebuild (optim_tc.cu)
 int update_pack(float* p, float* g, int rows, int cols, float lr, const float* scalars, __half* row_img, int64_t ld,
                 __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, bool write_g, cudaStream_t s);
 int rec_bwd_plan(int H, int B, RecPlan* plan);   // U = units per CTA, nCTA = 4 * clusters
 int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s);
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
-                 const float* cst, const float* c0, __half* dG_h, unsigned int* counter, int T, int B, int H, int G4p,
-                 MaskSrc m, cudaStream_t s, long long* trace = nullptr);
+                 const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
+                 int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace = nullptr);
 
 }  // namespace zrb
