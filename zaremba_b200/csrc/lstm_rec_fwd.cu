@@ -8,19 +8,23 @@
 // registers of the epilogue threads for the whole window.
 //
 // Per step:
-//   loader thread   waits on the grid barrier counter (acquire), then brings the 72 KB h_{t-1}
-//                   operand image (written by all CTAs, already in UMMA layout) into shared memory
-//                   as four cp.async.bulk pieces, each with its own mbarrier, so the MMAs start when
-//                   the first quarter of K has landed
-//   2 MMA threads   H/16 tcgen05.mma (M=64, N=pad8(B), K=16), even K steps by one thread into TMEM
-//                   accumulator 0, odd steps by another into accumulator 1.  tcgen05.mma has a ~45 clk
-//                   floor per instruction for any N <= 64 (profiles/r01_tcgen05_mma_issue_microbench.csv),
-//                   i.e. >= 4200 clk per step; a single issuing thread reaches only ~90 clk per MMA
-//   8 epilogue warps drain both accumulators through shared memory, add the x-part
-//                   pre-activations prefetched during the MMAs, apply sigmoid/tanh/cell update/dropout.
-//                   The next step's operand image is stored FIRST and published (fence + grid-barrier
-//                   arrival); everything backward needs (activated gates, c_t, row-major fp16 h,
-//                   dropout(h) for the next layer) is stored after the arrival, off the critical path.
+//   loader thread   polls the grid-barrier counter (relaxed loads, one fence.acquire.gpu after the last
+//                   arrival, fence.proxy.async.global), then brings the 72 KB h_{t-1} operand image (written
+//                   by all CTAs, already in UMMA layout; step 0: the image fwd_prep built from the incoming
+//                   state) into shared memory as four cp.async.bulk pieces, each with its own mbarrier, so
+//                   the MMAs start when the first quarter of K has landed
+//   4 MMA threads   H/16 tcgen05.mma (M=64, N=pad8(B), K=16); issuer i takes K steps i, i+4, ... into its
+//                   own TMEM accumulator.  One thread issuing back to back pays >= 44.6 clk per instruction
+//                   for any N <= 64 (profiles/r01_tcgen05_mma_issue_microbench.csv) and ~90 clk in a real
+//                   loop; four issuers reach 33 clk per MMA, the rate at which the tensor core fetches the
+//                   2.75 KB of operands of such an instruction from shared memory
+//   8 epilogue warps drain the accumulators (each warp sums all four of its lane quadrant / column group and
+//                   stages one value per row), add the x-part pre-activations prefetched during the MMAs,
+//                   apply sigmoid/tanh/cell update/dropout.  The next step's operand image is stored FIRST
+//                   and published (one red.release.gpu on the grid-barrier counter, which is never reset:
+//                   the launch gets its starting value); everything backward needs (activated gates, c_t,
+//                   row-major fp16 h, dropout(h) for the next layer) is stored after the arrival, off the
+//                   critical path.
 //
 // Roofline: latency/L2/shared-memory bound, not tensor bound -- per step each CTA streams its 144 KB
 // weight slice from shared memory through the tensor core (>= 1150 clk at 128 B/clk) and all CTAs

@@ -10,8 +10,9 @@ constexpr int kRecEpiWarps = 8;                       // warps 0-7: accumulator 
 constexpr int kRecEpiThreads = kRecEpiWarps * 32;
 constexpr int kRecMmaWarp = 8;                        // warps 8..11: lane 0 of warp 8+i issues K steps i, i+4, ... into its
 constexpr int kRecMmaWarps = 4;                       //   OWN accumulator i (warp 8 also owns the TMEM allocation).  8 issuers
-                                                      //   cut the MMA phase to ~2100 clk but the accumulator drain is bound by the
-                                                      //   64 B/clk TMEM read port, so 4 and 8 end up equal (measured)
+                                                      //   finish ISSUING in ~2100 clk, but the step did not get shorter:
+                                                      //   the MMAs complete at ~33 clk each either way and the drain has
+                                                      //   twice the accumulators to read
 constexpr int kRecLoadWarp = kRecMmaWarp + kRecMmaWarps;   // lane 0: grid-barrier wait + bulk copies
 constexpr int kRecThreads = (kRecLoadWarp + 1) * 32;
 constexpr int kRecTmemCols = 32 * kRecMmaWarps;       // one fp32 accumulator (N <= 32 columns) per issuer.  tcgen05.mma has a
