@@ -159,7 +159,10 @@ int  zrb_set_embed_rows_out(zrb_ctx* ctx, float* rows);
 /* Single-process fused step (zrb_train_step_grads/_update with the SAME grads buffers every step): touch only
  * this window's rows of the dense embedding gradient (clear the previous window's rows instead of zero-filling
  * 60 MB, take the norm over and update only the rows that can be non-zero).  The dense buffer stays exactly
- * what the full version would produce.  Not for data parallel runs that all-reduce the dense buffer. */
+ * what the full version would produce.  The same promise -- zrb_train_step_update sees the gradient buffers exactly
+ * as zrb_train_step_grads left them -- lets the tensor-core engine take the matrices' part of the clip norm from
+ * sums of squares its wgrad GEMM epilogues emitted (no second read of the gradients).  Not for data parallel runs
+ * that all-reduce the gradient buffers between the two calls. */
 int  zrb_set_embed_sparse(zrb_ctx* ctx, int32_t on);
 /* clip_grad_norm_ (main.py:115) scales the gradients in place, so after main.py:117 `.grad` holds coef * g.
  * on = 1 (default): zrb_train_step_update stores coef * g back like the reference.  on = 0: the update still
