@@ -23,6 +23,7 @@ struct zrb_tc_state {
     __half* hprev_h[ZRB_MAX_LAYERS] = {};
     __half* dG_h = nullptr;
     __half* dS_h = nullptr;
+    float* colsum_scratch = nullptr;   // row-split partials of the bias-gradient column sums
     int64_t packed_version = 0;
     zrb_params packed_params{};
     std::vector<void*> allocs;
@@ -86,6 +87,7 @@ int tc_ctx_init(zrb_ctx* c) {
     ZRB_TRY(tc_alloc(c, &t->fc_w_h, (size_t)V * t->Hp));
     ZRB_TRY(tc_alloc(c, &t->dG_h, N * t->G4p));
     ZRB_TRY(tc_alloc(c, &t->dS_h, N * t->Vp));
+    ZRB_TRY(tc_alloc(c, &t->colsum_scratch, (size_t)colsum_h_scratch_floats(V > 4 * H ? V : 4 * H)));
     ZRB_TRY(rec_fwd_plan(H, c->cfg.max_batch, &t->fplan));
     const char* force = getenv("ZRB_REC");
     if (force && !strcmp(force, "steps")) t->fplan.ok = 0;   // A/B switch: per-timestep launches
@@ -229,7 +231,7 @@ static int tc_backward_head(zrb_ctx* c, const zrb_params* p, const zrb_params* g
         t->wg_slots = 0;
         t->wg_key = g->fc_w;
         ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s, wgrad_sumsq(c, V, H, N)));
-        ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, nullptr, N, V, inv, s));
+        ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, nullptr, N, V, inv, t->colsum_scratch, s));
     }
     return ZRB_OK;
 }
@@ -284,7 +286,7 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
                             wgrad_sumsq(c, 4 * H, H, N)));
         ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->hprev_h[l], Hp, 1, g->w_hh[l], H, 4 * H, H, N, inv, nullptr, 0, s,
                             wgrad_sumsq(c, 4 * H, H, N)));
-        if (t->bplan.ok) ZRB_TRY(colsum_h(t->dG_h, G4p, g->b_ih[l], g->b_hh[l], N, 4 * H, inv, s));
+        if (t->bplan.ok) ZRB_TRY(colsum_h(t->dG_h, G4p, g->b_ih[l], g->b_hh[l], N, 4 * H, inv, t->colsum_scratch, s));
         else ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
         float* tmp = dY; dY = dX; dX = tmp;
     }

@@ -293,7 +293,7 @@ EncodeTiledFn get_encode() {
 }
 
 int g_num_sms = 0;
-bool g_attr_set[16] = {};
+bool g_attr_set[64][16] = {};   // per device: function attributes belong to the device's context
 
 }  // namespace
 
@@ -335,9 +335,12 @@ template <bool A_MN, bool B_MN, int GBN, int MT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
     auto kern = gemm_f16_tc_kernel<A_MN, B_MN, GBN, MT>;
     const int idx = (A_MN ? 2 : 0) + (B_MN ? 1 : 0) + (GBN == 256 ? 4 : 0) + (MT == 2 ? 8 : 0);
-    if (!g_attr_set[idx]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!g_attr_set[dev][idx]) {
         ZRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<GBN, MT>::kSmem));
-        g_attr_set[idx] = true;
+        g_attr_set[dev][idx] = true;
     }
     int grid = a.tiles_m * a.tiles_n * a.splits;
     if (grid > tc_num_sms()) grid = tc_num_sms();

@@ -367,10 +367,13 @@ int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
                  const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
                  int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};   // per device: function attributes belong to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!attr[dev]) {
         ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
+        attr[dev] = true;
     }
     RecBwdArgs a;
     a.base = counter_base;

@@ -303,10 +303,13 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
                  const float* c0, float* cst, float* h_last, float* c_last, __half* hprev_h, __half* y_h,
                  unsigned int* counter, unsigned int counter_base, int T, int B, int H, int Hp, MaskSrc m, cudaStream_t s,
                  long long* trace) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};   // per device: function attributes belong to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!attr[dev]) {
         ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
+        attr[dev] = true;
     }
     RecFwdArgs a;
     a.w_img = w_img; a.h0_img = h0_img; a.h_img = h_img; a.base = counter_base; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;

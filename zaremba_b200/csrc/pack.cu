@@ -102,15 +102,12 @@ __global__ void colsum_h_final_kernel(const float* __restrict__ part, float* __r
     out[j] = s * inv_scale;
     if (out2) out2[j] = s * inv_scale;
 }
-int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, cudaStream_t s) {
-    static float* scratch = nullptr;
-    static int scratch_cols = 0;
+int colsum_h_scratch_floats(int M) { return kRowSplit * ((M + 63) / 64 * 64); }
+
+// scratch: colsum_h_scratch_floats(M) floats owned by the caller's context (per device, per stream of use)
+int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, float* scratch,
+             cudaStream_t s) {
     const int Mp = (M + 63) / 64 * 64;
-    if (Mp > scratch_cols) {   // grown on first use / for a wider matrix; calls of one context share a stream
-        if (scratch) cudaFree(scratch);
-        ZRB_CUDA(cudaMalloc(&scratch, (size_t)kRowSplit * Mp * sizeof(float)));
-        scratch_cols = Mp;
-    }
     dim3 blk(32, 16), grid(Mp / 64, kRowSplit);
     colsum_h_partial_kernel<<<grid, blk, 0, s>>>(A, ld, scratch, N, M, Mp);
     ZRB_KERNEL_CHECK();

@@ -9,7 +9,9 @@ constexpr float kGradScale = 1024.f;   // fp16 gradient images hold kGradScale *
 
 int convert_pad_f16(const float* src, int64_t ld_src, __half* dst, int64_t ld_dst, int rows, int cols, float scale,
                     cudaStream_t s);
-int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, cudaStream_t s);
+int colsum_h_scratch_floats(int M);
+int colsum_h(const __half* A, int64_t ld, float* out, float* out2, int N, int M, float inv_scale, float* scratch,
+             cudaStream_t s);
 
 // cell pointwise with fp16 side outputs (tc_cell.cu)
 int lstm_cell_fwd_tc(float* pre, const float* c_prev, float* c_out, float* h_raw, __half* h_raw_h, __half* y_h,
