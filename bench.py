@@ -49,7 +49,21 @@ def flops_per_token(c):
     return 3 * (16 * c["L"] * c["H"] ** 2 + 2 * c["H"] * c["V"])
 
 
-def class_work(c):
+def clip_sgd_bytes(c, fused):
+    """Bytes the optimiser class has to move.  fused = the single-process `Trainer` step: the
+    matrices' sum of squares comes from the wgrad GEMM epilogues, coef*g is not stored back, only the window's
+    embedding rows are touched -> per matrix element 4 (g) + 4 + 4 (p read, write) + fp16 images; otherwise
+    (data parallel / keep_clipped_grads) the reference's passes: norm read 4 B + g read/write 8 B + p 8 B."""
+    N, H, L, V = c["T"] * c["B"], c["H"], c["L"], c["V"]
+    mats = L * 8 * H * H + V * H                       # w_ih, w_hh per layer + fc.W
+    small = L * 8 * H + V                              # biases
+    images = (L * 4 * H * H) * 2 + (L * 4 * H * H) * 4 + V * H * 2    # w_ih rows, w_hh fwd+bwd slices, fc rows
+    if fused:
+        return mats * 12 + images + small * 16 + N * H * 16
+    return (mats + V * H + small) * 20 + images
+
+
+def class_work(c, fused_update=True):
     """Algorithmic work of one step per kernel class: (kind, amount) with FLOPs for the dense
     contractions and bytes for the streaming kernels (DESIGN.md section 'Kernels')."""
     N, H, L, V = c["T"] * c["B"], c["H"], c["L"], c["V"]
@@ -59,7 +73,7 @@ def class_work(c):
         "proj_fwd": ("flop", 2 * N * H * V), "proj_bwd": ("flop", 4 * N * H * V),
         "rec_bwd": ("flop", 8 * N * H * H * L), "gemm_dx": ("flop", 8 * N * H * H * L),
         "gemm_wgrad": ("flop", 16 * N * H * H * L),
-        "softmax": ("byte", 2 * N * V * 4), "clip_sgd": ("byte", 20 * P),
+        "softmax": ("byte", N * V * 4 + N * V * 2), "clip_sgd": ("byte", clip_sgd_bytes(c, fused_update)),
         "embed_fwd": ("byte", 2 * N * H * 4), "embed_bwd": ("byte", V * H * 4 + 2 * N * H * 4),
         "pack": ("byte", 6 * (P - V * H - V)),
     }
@@ -107,10 +121,62 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def cpu_threads():
+    """torch's own default on an SMT box: half the logical CPUs (one per physical core)."""
+    n = os.cpu_count() or 2
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return max(1, n // 2)
+
+
+def bench_config(name, c, world, engine, transport, device):
+    """`config` object shared by both arms (same keys, so the driver can compare them)."""
+    return {"workload": workload_name(name, c), "device": device, "engine": engine, "parallelism": f"dp{world}",
+            "dp_transport": transport, "global_batch": c["B"] * world, "seq_len": c["T"],
+            "l2": "no flush: per-step working set (fp32 params+grads 528 MB + activations) exceeds the 126 MB L2"
+            if name == "large" else "no flush; working set may fit L2 for this config"}
+
+
+def gpu_baseline_leg(c, steps=40, warmup=10):
+    """The bar BASELINE.json's north_star names: the reference's `--lstm_type pytorch` train step on the SAME GPU
+    (oracle/torch_port.py on cuda = the reference's own torch calls: cuDNN nn.LSTM, cuBLAS addmm, eager softmax,
+    clip_grad_norm_, per-parameter SGD; torch default flags), CUDA-event timed, tokens handed over as CPU views
+    like main.py:111 does."""
+    import torch
+    from oracle import torch_port as P
+    model = P.TorchLstmLm(c["V"], c["H"], c["L"], c["p"], c["winit"], seed=1).cuda()
+    model.train()
+    data = P.synthetic_batches(c["V"], c["B"], c["T"], steps + warmup)
+    states = model.zero_state(c["B"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i, (x, y) in enumerate(data):
+        if i == warmup:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+        _, _, states = P.train_step(model, x.cuda(), y.cuda(), states, c["lr"], c["clip"])
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    ms = e0.elapsed_time(e1) / steps
+    del model
+    torch.cuda.empty_cache()
+    return {"value": c["T"] * c["B"] / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "ms_per_step_wall": wall,
+            "steps": steps, "warmup": warmup, "n_gpus": 1,
+            "what": "reference --lstm_type pytorch path (cuDNN nn.LSTM + cuBLAS + eager loss/clip/SGD) on this GPU, "
+                    f"torch {torch.__version__}, cuDNN {torch.backends.cudnn.version()}, "
+                    f"cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, matmul tf32={torch.backends.cuda.matmul.allow_tf32}"}
+
+
 def cpu_port_leg(c, budget_s, steps=None, warmup=1):
     """The reference's CPU path (torch port) on the host cores; bounded sample."""
     import torch
     from oracle import torch_port as P
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference's CPU path (`main.py --device cpu`) uses torch's
+    # default = one thread per physical core, so pin that here and the arm means the same thing at every N
+    torch.set_num_threads(cpu_threads())
     if steps is None:
         dt1, _, thr = P.time_cpu_train_steps(c["V"], c["H"], c["L"], c["B"], c["T"], c["p"], c["winit"], c["lr"],
                                              c["clip"], steps=1, warmup=1)
@@ -134,7 +200,7 @@ def run_reference(args, c, name):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(name, c), "device": "host CPU"},
+            "config": bench_config(name, c, max(1, args.gpus), "torch CPU (oneDNN)", None, "host CPU"),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -203,6 +269,21 @@ def run_ours(args, c, name):
     dev_ms, _, launches = timed_region(lambda x, y: tr.train_step(x, y, c["lr"], c["clip"]), dev_batches)
     clocks = sampler.stop() if sampler else None
     loss_after = tr.loss.item()
+    # replica check: after the timed steps every rank must hold bit-identical parameters (same all-reduced
+    # gradients, same clip, same update) -- MAX - MIN over ranks of two checksums, must be 0
+    dp_check = None
+    if world > 1:
+        bits = tr.flat_p.view(torch.int32).to(torch.int64)
+        chk = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dp_check = {"param_checksum_max_minus_min": [int(v) for v in (hi - lo).tolist()],
+                    "replicas_identical": bool((hi == lo).all().item()), "after_steps": K + W}
+    # the same step in the mode that leaves coef * g in .grad like clip_grad_norm_ (main.py:115) does
+    _lib.check(lib.zrb_set_keep_clipped_grads(tr.ctx, 1))
+    keep_ms, _, _ = timed_region(lambda x, y: tr.train_step(x, y, c["lr"], c["clip"]), dev_batches)
+    _lib.check(lib.zrb_set_keep_clipped_grads(tr.ctx, 1 if tr._keep_clipped else 0))
     # 2) end to end through the host-buffer call (wall clock: H2D, step, D2H of the loss each step)
     tr.reset_states()
     _, e2e_wall_ms, _ = timed_region(lambda x, y: tr.train_step_host(x, y, c["lr"], c["clip"]), host_batches)
@@ -224,7 +305,7 @@ def run_ours(args, c, name):
         return
     tokens = T * B * world * K
     peaks = measured_peaks()
-    work = class_work(c)
+    work = class_work(c, fused_update=(world == 1))
     top = max(per_class, key=lambda n: per_class[n][0]) if per_class else None
     roofline = None
     if top:
@@ -250,16 +331,30 @@ def run_ours(args, c, name):
         "metric": METRIC, "value": tokens / (dev_ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands, f32 accumulate/state" if args.engine == "tc" else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(name, c), "engine": args.engine, "parallelism": f"dp{world}", "dp_transport": getattr(tr, "transport", None),
-                   "global_batch": B * world, "seq_len": T,
-                   "l2": "no flush: per-step working set (fp32 params+grads 528 MB + activations) exceeds the 126 MB L2"
-                   if name == "large" else "no flush; working set may fit L2 for this config"},
+        "config": bench_config(name, c, world, args.engine, getattr(tr, "transport", None), "B200"),
         "e2e": {"value": tokens / (e2e_wall_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_wall_ms / K,
                 "h2d_bytes_per_step": 2 * T * B * 8, "d2h_bytes_per_step": 8,
                 "api": "zaremba_b200.Trainer.train_step_host -> zrb_train_step_host"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "final_loss": loss_after,
         "flops_per_token": flops_per_token(c),
+        "keep_clipped_grads_mode": {"ms_per_step": keep_ms / K, "value": tokens / (keep_ms * 1e-3),
+                                    "note": "same step with coef*g stored back into .grad like clip_grad_norm_ "
+                                            "(main.py:115); `value` is the default mode that skips the dead store"},
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    if not args.no_gpu_baseline:
+        # the north_star's bar on the same GPU, timed right after ours with its own clock sample
+        s2 = ClockSampler(local)
+        s2.start()
+        gb = gpu_baseline_leg(c)
+        gb["clocks"] = s2.stop()
+        line["gpu_baseline"] = gb
+        line["vs_baseline"] = line["value"] / gb["value"]
+        line["vs_baseline_note"] = ("value / gpu_baseline.value: BASELINE.md publishes no tokens/s; the bar the "
+                                    "north_star names is the reference's cuDNN path on the same B200 (single device: "
+                                    "the reference has no multi-GPU path), measured in this run")
+        line["e2e"]["vs_gpu_baseline"] = line["e2e"]["value"] / gb["value"]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_port_leg(c, args.cpu_budget)
     print(json.dumps(line), flush=True)
@@ -277,6 +372,7 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("ZRB_ENGINE", "tc"), choices=["tc", "simt"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     c = CONFIGS[args.config]

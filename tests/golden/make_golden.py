@@ -138,6 +138,10 @@ def step_case(name, V, H, L, T, B, lstm_type, dropout, winit, seed, lr, max_norm
                 g64 = g.astype(np.float64)
                 out[pre + "grad_l2/" + k] = np.array(np.sqrt((g64 * g64).sum()))
                 out[pre + "grad_head/" + k] = g.reshape(-1)[:32].copy()
+            for k, v in model.state_dict().items():      # parameters after the update of main.py:116-117
+                a = _np(v).astype(np.float64)
+                out[pre + "param_sum/" + k] = np.array([a.sum(), np.abs(a).sum(), (a * a).sum()])
+                out[pre + "param_head/" + k] = _np(v).reshape(-1)[:32].copy()
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
@@ -199,16 +203,29 @@ def perplexity_case():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    #         name               V    H  L  T  B  type      p    winit seed lr  clip
-    step_case("tiny_pytorch",    37, 16, 2, 5, 3, "pytorch", 0.0, 0.3, 11, 1.0, 0.25)
-    step_case("tiny_custom",     37, 16, 2, 5, 3, "custom",  0.0, 0.3, 12, 1.0, 0.25)
-    step_case("tiny_dropout",    41, 24, 2, 6, 4, "pytorch", 0.5, 0.3, 13, 0.5, 5.0, steps=2)
-    step_case("tiny_carry3",     29, 20, 3, 4, 2, "pytorch", 0.0, 0.2, 14, 1.0, 10.0, steps=3, zero_state=True)
-    step_case("edge_T1_B1_L1",   17,  8, 1, 1, 1, "pytorch", 0.0, 0.5, 15, 1.0, 1.0)
-    step_case("odd_H40_custom_dropout", 53, 40, 2, 3, 5, "custom", 0.65, 0.2, 16, 1.0, 2.0)
-    step_case("mid_H72",        150,  72, 2, 20, 20, "pytorch", 0.0, 0.1, 17, 1.0, 5.0, zero_state=True)
-    # BASELINE.json configs[0] shape (2x200, seq 20, bs 20, V=10000): summaries only, weights re-derived from the seed
-    step_case("small_cfg_summary", 10000, 200, 2, 20, 20, "pytorch", 0.0, 0.1, 1, 1.0, 5.0,
-              steps=2, zero_state=True, store_full=False)
-    minibatch_case()
-    perplexity_case()
+    only = set(sys.argv[1:])                     # optional: mint only the named fixtures
+
+    def case(name, *a, **kw):
+        if not only or name in only:
+            step_case(name, *a, **kw)
+
+    #    name               V    H  L  T  B  type      p    winit seed lr  clip
+    case("tiny_pytorch",    37, 16, 2, 5, 3, "pytorch", 0.0, 0.3, 11, 1.0, 0.25)
+    case("tiny_custom",     37, 16, 2, 5, 3, "custom",  0.0, 0.3, 12, 1.0, 0.25)
+    case("tiny_dropout",    41, 24, 2, 6, 4, "pytorch", 0.5, 0.3, 13, 0.5, 5.0, steps=2)
+    case("tiny_carry3",     29, 20, 3, 4, 2, "pytorch", 0.0, 0.2, 14, 1.0, 10.0, steps=3, zero_state=True)
+    case("edge_T1_B1_L1",   17,  8, 1, 1, 1, "pytorch", 0.0, 0.5, 15, 1.0, 1.0)
+    case("odd_H40_custom_dropout", 53, 40, 2, 3, 5, "custom", 0.65, 0.2, 16, 1.0, 2.0)
+    case("mid_H72",        150,  72, 2, 20, 20, "pytorch", 0.0, 0.1, 17, 1.0, 5.0, zero_state=True)
+    # BASELINE.json configs[0..2] at their exact shapes (README.md:20-27 recipes, V=10000): summaries only, weights
+    # re-derived from the seed, the reference's dropout masks stored bit-packed
+    case("small_cfg_summary", 10000, 200, 2, 20, 20, "pytorch", 0.0, 0.1, 1, 1.0, 5.0,
+         steps=2, zero_state=True, store_full=False)
+    case("medium_cfg_summary", 10000, 650, 2, 35, 20, "pytorch", 0.5, 0.05, 1, 1.0, 5.0,
+         steps=2, zero_state=True, store_full=False)
+    case("large_cfg_summary", 10000, 1500, 2, 35, 20, "pytorch", 0.65, 0.04, 1, 1.0, 10.0,
+         steps=2, zero_state=True, store_full=False)
+    if not only or "minibatch" in only:
+        minibatch_case()
+    if not only or "perplexity_ptb_slice" in only:
+        perplexity_case()

@@ -33,8 +33,25 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile and link.  Serialised with a file lock: under torchrun every rank imports the package at the same
+    time, and concurrent nvcc runs into the same .o / .so files would corrupt the library; the ranks that lose
+    the race wait for the lock, re-check the timestamps and find the library current."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -56,10 +73,12 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    os.replace(tmp, LIB)           # atomic: a process that is loading the old library keeps a consistent file
     return LIB
 
 

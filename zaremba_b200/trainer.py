@@ -63,6 +63,8 @@ class Trainer:
         default = "ce" if self.world <= 4 else "nccl"
         self.transport = os.environ.get("ZRB_DP_TRANSPORT", default) if self.world > 1 else None
         self._dp = None
+        if self.transport == "ce" and not self._ce_supported():
+            self.transport = "nccl"        # multi-node run or no P2P between the GPUs: one NCCL all-reduce instead
         if self.transport == "ce":
             self.flat_g = self._create_ce_transport(sum(sizes))
         else:
@@ -86,7 +88,11 @@ class Trainer:
         self._hy = torch.empty(seq_length, batch_size, dtype=torch.int64).pin_memory()
         self._hloss = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.step = 0
-        self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        # Dropout keep-flags are Philox(seed, step, site, element).  Data-parallel ranks hold different rows of the
+        # global batch, so each rank needs its own stream of flags (identical weights, which bench.py / train_ptb.py
+        # get from a common torch seed, must not imply identical masks): the rank is folded into the key.
+        rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.seed = (int(torch.initial_seed()) + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
         # data-parallel buckets of the flat gradient buffer, in the order backward completes them:
         # [fc.W, fc.b], layer L-1, ..., layer 1, [embed.W + layer 0]
         L = model.layer_num
@@ -113,6 +119,19 @@ class Trainer:
             self._rows_all = torch.zeros(self.world * N, H, device=dev)
             self._ids_all = torch.zeros(self.world * N, dtype=torch.int64, device=dev)
             # (the rows buffer is handed to the context only for the duration of a DP step, see _grads_ce)
+
+    def _ce_supported(self):
+        """The copy-engine transport needs every rank on ONE host (CUDA IPC) with peer access between all GPUs.
+        Decided collectively so that all ranks pick the same transport."""
+        import socket
+        info = [None] * self.world
+        dist.all_gather_object(info, (socket.gethostname(), self.dev.index), group=self.pg)
+        ok = len({h for h, _ in info}) == 1
+        if ok:
+            ok = all(i == self.dev.index or torch.cuda.can_device_access_peer(self.dev.index, i) for _, i in info)
+        flag = torch.tensor([1 if ok else 0], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+        return bool(flag.item())
 
     def _create_ce_transport(self, n):
         """zrb_dp_create + CUDA-IPC handle exchange; returns the library-owned flat gradient buffer as a tensor."""
@@ -182,6 +201,34 @@ class Trainer:
             self._ctx_cached = c.value
         return c
 
+    def params_changed(self):
+        """Tell the library that parameter VALUES were changed outside it (model.load_state_dict, a manual edit):
+        the fp16 operand images are rebuilt on the next step.  train_step / eval_step also detect in-place writes
+        through the tensors' version counters, so calling this is only needed after writes torch cannot see."""
+        _lib.check(_lib.load().zrb_params_changed(self.ctx))
+        self._versions = self._param_versions()
+
+    def _param_versions(self):
+        return tuple(p._version for p in self.model.parameters())
+
+    def _check_versions(self):
+        v = self._param_versions()
+        if v != getattr(self, "_versions", None):
+            _lib.check(_lib.load().zrb_params_changed(self.ctx))
+            self._versions = v
+
+    def close(self):
+        """Release the copy-engine transport (IPC mappings, streams)."""
+        if getattr(self, "_dp", None) is not None:
+            _lib.load().zrb_dp_destroy(self._dp)
+            self._dp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def reset_states(self):
         for h, c in self.states:
             h.zero_(); c.zero_()
@@ -195,6 +242,7 @@ class Trainer:
         tensors (no host sync)."""
         lib = _lib.load()
         T, B = x.shape
+        self._check_versions()
         if self.world > 1 and self.transport == "ce":
             self._grads_ce(lib, x, y, T, B)
         elif self.world > 1 and self.overlap:
@@ -205,6 +253,10 @@ class Trainer:
                                                 self.step, _lib.ptr(self.loss), self._stream()))
             if self.world > 1:
                 allreduce_sum_(self.flat_g, self.pg)
+        if self._dp is not None and self._keep_clipped:
+            # the update rewrites g in place (coef * g) while peers may still be pulling this rank's reduced shards
+            # out of it: wait for every peer's "done" flag first (the wait the next step's first write does anyway)
+            _lib.check(lib.zrb_dp_begin_step(self._dp, self._stream()))
         _lib.check(lib.zrb_train_step_update(self.ctx, C.byref(self._ps), C.byref(self._gs), float(lr),
                                              float(max_norm), _lib.ptr(self.norm), self._stream()))
         self.step += 1
@@ -251,6 +303,7 @@ class Trainer:
             hx = torch.empty(T, B, dtype=torch.int64).pin_memory(); hy = torch.empty_like(hx).pin_memory()
         hx.copy_(x); hy.copy_(y)
         if self.world == 1:
+            self._check_versions()
             _lib.check(lib.zrb_train_step_host(self.ctx, C.byref(self._ps), C.byref(self._gs),
                                                C.c_void_p(hx.data_ptr()), C.c_void_p(hy.data_ptr()), T, B,
                                                C.byref(self._st), C.byref(self._st), self.seed, self.step,
@@ -270,6 +323,7 @@ class Trainer:
         (ensemble.py:100-106)."""
         lib = _lib.load()
         T, B = x.shape
+        self._check_versions()
         _lib.check(lib.zrb_eval_step(self.ctx, C.byref(self._ps), _lib.ptr(x), _lib.ptr(y), T, B,
                                      C.byref(self._st), C.byref(self._st), _lib.ptr(self.loss),
                                      _lib.ptr(self.tgt_prob) if want_probs else None, self._stream()))
