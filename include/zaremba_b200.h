@@ -164,6 +164,10 @@ int  zrb_set_embed_rows_out(zrb_ctx* ctx, float* rows);
  * sums of squares its wgrad GEMM epilogues emitted (no second read of the gradients).  Not for data parallel runs
  * that all-reduce the gradient buffers between the two calls. */
 int  zrb_set_embed_sparse(zrb_ctx* ctx, int32_t on);
+/* on = 2: the rows-only half alone, for data-parallel steps that all-reduce the gradient buffers between _grads and
+ * _update (the epilogue sums of squares describe the LOCAL gradients, so the norm is taken over the reduced buffers):
+ * zrb_embed_scatter_rows then clears only the rows the previous step touched and remembers this step's ids (all
+ * ranks' tokens), and zrb_train_step_update takes the norm over / updates only those rows of embed.W. */
 /* clip_grad_norm_ (main.py:115) scales the gradients in place, so after main.py:117 `.grad` holds coef * g.
  * on = 1 (default): zrb_train_step_update stores coef * g back like the reference.  on = 0: the update still
  * applies p -= lr * coef * g but leaves the gradient buffers as backward wrote them (the scaled gradients are
@@ -194,6 +198,14 @@ int    zrb_dp_begin_step(zrb_dp* dp, void* stream);
 int    zrb_dp_allreduce_bucket(zrb_dp* dp, int32_t bucket, int64_t lo, int64_t hi, int32_t last, void* stream);
 /* join: `stream` waits for all bucket reductions enqueued in this step (alternative to last = 1) */
 int    zrb_dp_finish_step(zrb_dp* dp, void* stream);
+
+/* Co-scheduling hook for work that must only use the SMs the persistent backward recurrence leaves idle (the
+ * data-parallel bucket all-reduce of a communicator limited to <= 16 CTAs): the kernel's CTA 0 stores a sequence
+ * number into a device flag once every CTA of its grid is resident.  zrb_resident_flag returns the flag and the value
+ * the NEXT backward-recurrence launch of this context will publish (0: this context does not use the persistent
+ * kernel, do not wait); zrb_stream_wait_value32 makes `stream` wait until *d_flag >= value (cuStreamWaitValue32). */
+int  zrb_resident_flag(zrb_ctx* ctx, uint32_t** d_flag, uint32_t* next_value);
+int  zrb_stream_wait_value32(void* stream, const uint32_t* d_flag, uint32_t value);
 
 /* perplexity's inner step (main.py:91-94) without materialising scores for the caller:
  * forward in eval mode + loss (+ per-token target probabilities for the ensemble). */

@@ -35,7 +35,7 @@ pytestmark = pytest.mark.gpu
 ENGINES = os.environ.get("ZRB_TEST_ENGINES", "simt,tc").split(",")
 CASES = ["small_cfg_summary", "medium_cfg_summary", "large_cfg_summary"]
 TOL = {"simt": dict(loss=2e-5, fwd=5e-5, l2=1e-4, head=2e-3, psum=2e-6),
-       "tc": dict(loss=3e-4, fwd=1.5e-3, l2=1.5e-3, head=1e-2, psum=2e-5)}
+       "tc": dict(loss=3e-4, fwd=1.5e-3, l2=1.5e-3, head=1e-2, psum=1e-4)}
 MEASURED = {}      # filled while the tests run; written by the last test for profiles/
 
 

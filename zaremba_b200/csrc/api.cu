@@ -115,6 +115,9 @@ int zrb_ctx_create(const zrb_config* cfg, zrb_ctx** out) {
     if (rc == ZRB_OK) rc = dalloc(c, &c->scalars, 16);
     if (rc == ZRB_OK) rc = dalloc(c, &c->x_saved, N);
     if (rc == ZRB_OK) rc = dalloc(c, &c->emb_prev_ids, N);
+    if (rc == ZRB_OK) c->emb_prev_cap = (int64_t)N;
+    if (rc == ZRB_OK) rc = dalloc(c, &c->resident_flag, 4);
+    if (rc == ZRB_OK && cudaMemset(c->resident_flag, 0, 4 * sizeof(unsigned int)) != cudaSuccess) rc = ZRB_E_CUDA;
     if (rc == ZRB_OK) rc = dalloc(c, &c->emb_first, (size_t)V);
     if (rc == ZRB_OK) rc = dalloc(c, &c->y_dev, N);
     if (rc == ZRB_OK) rc = dalloc(c, &c->x_dev, N);
@@ -275,8 +278,17 @@ int zrb_set_keep_clipped_grads(zrb_ctx* c, int32_t on) {
 
 int zrb_set_embed_sparse(zrb_ctx* c, int32_t on) {
     ZRB_REQUIRE(c, "null ctx");
+    ZRB_REQUIRE(on >= 0 && on <= 2, "mode must be 0, 1 or 2");
     c->emb_sparse = on != 0;
+    c->fused_norm = on == 1;
     c->emb_prev_grad = nullptr;
+    return ZRB_OK;
+}
+
+int zrb_resident_flag(zrb_ctx* c, uint32_t** flag, uint32_t* next_value) {
+    ZRB_REQUIRE(c && flag && next_value, "null argument");
+    *flag = c->resident_flag;
+    *next_value = (c->cfg.engine == ZRB_ENGINE_TC && tc_persistent_bwd(c)) ? c->resident_seq + 1 : 0;
     return ZRB_OK;
 }
 
@@ -295,8 +307,23 @@ int zrb_embed_scatter_rows(zrb_ctx* c, float* grad_embed, const int64_t* ids, co
         c->emb_cap_rows = n_rows;
     }
     ProfScope ps(c, ZRB_PROF_EMBED_BWD, s);
-    ZRB_CUDA(cudaMemsetAsync(grad_embed, 0, (size_t)c->cfg.vocab * c->cfg.hidden * sizeof(float), s));
-    return embed_scatter_rows(ids, rows, grad_embed, (int)n_rows, c->cfg.hidden, c->cfg.vocab, c->emb_first, c->emb_acc, s);
+    const int H = c->cfg.hidden, V = c->cfg.vocab;
+    if (c->emb_sparse && c->emb_prev_grad == grad_embed) {
+        ZRB_TRY(embed_zero_rows(grad_embed, c->emb_prev_ids, c->emb_prev_n, H, V, s));   // only the last step's rows are non-zero
+    } else {
+        ZRB_CUDA(cudaMemsetAsync(grad_embed, 0, (size_t)V * H * sizeof(float), s));
+    }
+    ZRB_TRY(embed_scatter_rows(ids, rows, grad_embed, (int)n_rows, H, V, c->emb_first, c->emb_acc, s));
+    if (c->emb_sparse) {   // zrb_train_step_update then takes the norm over / updates these rows only
+        if (n_rows > c->emb_prev_cap) {
+            ZRB_TRY(dalloc(c, &c->emb_prev_ids, (size_t)n_rows));
+            c->emb_prev_cap = n_rows;
+        }
+        ZRB_CUDA(cudaMemcpyAsync(c->emb_prev_ids, ids, (size_t)n_rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+        c->emb_prev_n = (int)n_rows;
+        c->emb_prev_grad = grad_embed;
+    }
+    return ZRB_OK;
 }
 
 int zrb_train_step_update(zrb_ctx* c, const zrb_params* p, const zrb_params* g, float lr, float max_norm,

@@ -47,7 +47,11 @@ struct zrb_ctx {
     long long* emb_acc = nullptr;
     int64_t emb_cap_rows = 0;
     bool keep_clipped = true;              // zrb_train_step_update writes coef * g back into the gradient buffers
-    bool emb_sparse = false;               // fused single-process step: touch only this window's embedding rows
+    bool emb_sparse = false;               // touch only the rows of the embedding gradient that can be non-zero
+    bool fused_norm = false;               // single process: matrices' part of the clip norm from the wgrad GEMM epilogues
+    int64_t emb_prev_cap = 0;              // capacity of emb_prev_ids (tokens)
+    unsigned int* resident_flag = nullptr; // written by the backward recurrence kernel once all its CTAs are resident
+    unsigned int resident_seq = 0;         // value the last launch publishes there
     int64_t* emb_prev_ids = nullptr;       // token ids whose gradient rows are non-zero in emb_prev_grad
     int emb_prev_n = 0;
     float* emb_prev_grad = nullptr;
@@ -91,6 +95,7 @@ int tc_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
                         float* loss, cudaStream_t s);
 int tc_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int l, cudaStream_t s);
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries);
+bool tc_persistent_bwd(const zrb_ctx* c);   // the persistent backward recurrence kernel is in use for this context
 int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
               cudaStream_t s);
 

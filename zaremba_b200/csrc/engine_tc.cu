@@ -21,8 +21,14 @@ struct zrb_tc_state {
     __half* fc_w_h = nullptr;
     __half* x_h[ZRB_MAX_LAYERS + 1] = {};
     __half* hprev_h[ZRB_MAX_LAYERS] = {};
-    __half* dG_h = nullptr;
+    __half* dG_h = nullptr;            // scaled dG of the layer being differentiated ...
+    __half* dG_h_alt = nullptr;        // ... double-buffered by layer parity: the weight gradients of layer l run
+                                       //     underneath the recurrence of layer l-1, which writes the other buffer
     __half* dS_h = nullptr;
+    // weight-gradient GEMMs deferred to run as programmatic dependents of the NEXT backward recurrence kernel (on the
+    // ~20 SMs it leaves idle): 0 none, 1 = fc.W, 2 = (w_ih, w_hh) of layer `pending_layer`
+    int pending = 0, pending_layer = 0;
+    bool defer_wgrad = false;
     float* colsum_scratch = nullptr;   // row-split partials of the bias-gradient column sums
     int64_t packed_version = 0;
     zrb_params packed_params{};
@@ -86,6 +92,7 @@ int tc_ctx_init(zrb_ctx* c) {
     for (int l = 0; l <= L; ++l) ZRB_TRY(tc_alloc(c, &t->x_h[l], N * t->Hp));
     ZRB_TRY(tc_alloc(c, &t->fc_w_h, (size_t)V * t->Hp));
     ZRB_TRY(tc_alloc(c, &t->dG_h, N * t->G4p));
+    ZRB_TRY(tc_alloc(c, &t->dG_h_alt, N * t->G4p));
     ZRB_TRY(tc_alloc(c, &t->dS_h, N * t->Vp));
     ZRB_TRY(tc_alloc(c, &t->colsum_scratch, (size_t)colsum_h_scratch_floats(V > 4 * H ? V : 4 * H)));
     ZRB_TRY(rec_fwd_plan(H, c->cfg.max_batch, &t->fplan));
@@ -226,12 +233,46 @@ static int tc_backward_head(zrb_ctx* c, const zrb_params* p, const zrb_params* g
         ProfScope ps(c, ZRB_PROF_PROJ_BWD, s);
         // dA[N,H] = dS[N,V] * W[V,H]       (W image read MN-major)
         ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 0, t->fc_w_h, Hp, 1, dY, H, N, H, V, inv, nullptr, 0, s));
-        // dW[V,H] = dS^T[V,N] * A[N,H]     (both operands MN-major: contraction over tokens)
-        t->wg_ok = c->emb_sparse;
+        t->wg_ok = c->fused_norm;
         t->wg_slots = 0;
         t->wg_key = g->fc_w;
-        ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s, wgrad_sumsq(c, V, H, N)));
         ZRB_TRY(colsum_h(t->dS_h, Vp, g->fc_b, nullptr, N, V, inv, t->colsum_scratch, s));
+        // dW[V,H] = dS^T[V,N] * A[N,H]     (both operands MN-major: contraction over tokens).  Nothing downstream in
+        // backward reads it: with deferral on it runs underneath the first backward recurrence instead of before it.
+        t->pending = 0;
+        if (t->defer_wgrad && t->bplan.ok && !c->prof_on) t->pending = 1;
+        else ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s,
+                                 wgrad_sumsq(c, V, H, N)));
+    }
+    return ZRB_OK;
+}
+
+// the two weight gradients of layer l from dG (scaled fp16, [N,G4p]): ONE launch, dG is the shared A operand
+static int tc_layer_wgrads(zrb_ctx* c, const zrb_params* g, int l, const __half* dG_h, bool pdl, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, N = c->T * c->B;
+    float* ss1 = wgrad_sumsq(c, 4 * H, H, N);
+    float* ss2 = wgrad_sumsq(c, 4 * H, H, N);
+    return gemm_f16_tc(dG_h, t->G4p, 1, t->x_h[l], t->Hp, 1, g->w_ih[l], H, 4 * H, H, N, 1.f / kGradScale, nullptr, 0, s,
+                       ss1, nullptr, pdl, t->hprev_h[l], g->w_hh[l], ss2);
+}
+
+// launch what tc_backward_head / the previous layer deferred, as a programmatic dependent of the recurrence kernel
+// that was just enqueued on `s`
+static int tc_issue_pending(zrb_ctx* c, const zrb_params* g, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab, N = c->T * c->B;
+    const int kind = t->pending;
+    t->pending = 0;
+    if (kind == 1) {
+        ProfScope ps(c, ZRB_PROF_PROJ_BWD, s);
+        return gemm_f16_tc(t->dS_h, t->Vp, 1, t->x_h[L], t->Hp, 1, g->fc_w, H, V, H, N, 1.f / kGradScale, nullptr, 0, s,
+                           wgrad_sumsq(c, V, H, N), nullptr, true);
+    }
+    if (kind == 2) {
+        ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
+        const int l = t->pending_layer;
+        return tc_layer_wgrads(c, g, l, (l & 1) ? t->dG_h_alt : t->dG_h, true, s);
     }
     return ZRB_OK;
 }
@@ -250,6 +291,7 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
     }
     float* dY = c->bwd_dy;
     float* dX = c->bwd_dx;
+    __half* dG_h = (l & 1) ? t->dG_h_alt : t->dG_h;
     {
         MaskSrc m = site_mask(c, l + 1);
         if (t->bplan.ok) {
@@ -259,10 +301,12 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
                 ZRB_CUDA(cudaMemsetAsync(t->counter + 32, 0, sizeof(unsigned int), s));
                 t->cnt_b = 0;
             }
-            ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], t->dG_h,
+            ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], dG_h,
                                  t->counter + 32, t->cnt_b, T, B, H, G4p, m, s,
-                                 t->trace ? t->trace + (size_t)c->cfg.max_seq * 8 : nullptr));
+                                 t->trace ? t->trace + (size_t)c->cfg.max_seq * 8 : nullptr, g->b_ih[l], g->b_hh[l],
+                                 c->resident_flag, ++c->resident_seq));
             t->cnt_b += arrivals;
+            ZRB_TRY(tc_issue_pending(c, g, s));   // runs on the SMs the cluster kernel leaves idle
         } else {
             ProfScope ps(c, ZRB_PROF_REC_BWD, s);
             ZRB_CUDA(cudaMemsetAsync(c->dc, 0, bh * sizeof(float), s));   // (the persistent kernel keeps dc in registers)
@@ -270,24 +314,27 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
                 const float* c_prev = tt ? c->cst[l] + (size_t)(tt - 1) * bh : c->c0s[l];
                 ZRB_TRY(lstm_cell_bwd_tc(dY + (size_t)tt * bh, tt == T - 1 ? nullptr : c->dh_rec, c->dc,
                                          c->gates[l] + (size_t)tt * B * 4 * H, c->cst[l] + (size_t)tt * bh, c_prev,
-                                         c->dG + (size_t)tt * B * 4 * H, t->dG_h + (size_t)tt * B * G4p, G4p, B, H,
+                                         c->dG + (size_t)tt * B * 4 * H, dG_h + (size_t)tt * B * G4p, G4p, B, H,
                                          (int64_t)tt * bh, (int64_t)N * H, m, s));
                 if (tt > 0)  // dh_{t-1}[B,H] = dG_t[B,4H] * W_hh[4H,H]
-                    ZRB_TRY(gemm_f16_tc(t->dG_h + (size_t)tt * B * G4p, G4p, 0, t->w_hh_h[l], Hp, 1, c->dh_rec, H, B, H,
+                    ZRB_TRY(gemm_f16_tc(dG_h + (size_t)tt * B * G4p, G4p, 0, t->w_hh_h[l], Hp, 1, c->dh_rec, H, B, H,
                                         4 * H, inv, nullptr, 0, s));
             }
         }
         {
             ProfScope ps(c, ZRB_PROF_GEMM_DX, s);
-            ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 0, t->w_ih_h[l], Hp, 1, dX, H, N, H, 4 * H, inv, nullptr, 0, s));
+            ZRB_TRY(gemm_f16_tc(dG_h, G4p, 0, t->w_ih_h[l], Hp, 1, dX, H, N, H, 4 * H, inv, nullptr, 0, s));
         }
-        ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
-        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->x_h[l], Hp, 1, g->w_ih[l], H, 4 * H, H, N, inv, nullptr, 0, s,
-                            wgrad_sumsq(c, 4 * H, H, N)));
-        ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->hprev_h[l], Hp, 1, g->w_hh[l], H, 4 * H, H, N, inv, nullptr, 0, s,
-                            wgrad_sumsq(c, 4 * H, H, N)));
-        if (t->bplan.ok) ZRB_TRY(colsum_h(t->dG_h, G4p, g->b_ih[l], g->b_hh[l], N, 4 * H, inv, t->colsum_scratch, s));
-        else ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
+        // dW_ih, dW_hh: nothing downstream in backward reads them -> for l > 0 they run underneath the next layer's
+        // recurrence (which writes the other dG buffer); the bias gradients come out of the recurrence kernel itself
+        if (t->defer_wgrad && t->bplan.ok && l > 0 && !c->prof_on) {
+            t->pending = 2;
+            t->pending_layer = l;
+        } else {
+            ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
+            ZRB_TRY(tc_layer_wgrads(c, g, l, dG_h, false, s));
+        }
+        if (!t->bplan.ok) ZRB_TRY(colsum(c->dG, g->b_ih[l], g->b_hh[l], N, 4 * H, s));
         float* tmp = dY; dY = dX; dX = tmp;
     }
     c->bwd_dy = dY;
@@ -311,6 +358,8 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
 }
 
 static int tc_backward_from_image(zrb_ctx* c, const zrb_params* p, const zrb_params* g, cudaStream_t s) {
+    static const bool no_overlap = getenv("ZRB_NO_OVERLAP") != nullptr;    // A/B switch
+    c->tc->defer_wgrad = !no_overlap;
     ZRB_TRY(tc_backward_head(c, p, g, s));
     for (int l = c->cfg.layers - 1; l >= 0; --l) ZRB_TRY(tc_backward_layer(c, p, g, l, s));
     return ZRB_OK;
@@ -350,12 +399,15 @@ int tc_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
         ZRB_TRY(softmax_nll(c->scores, y, T * B, c->cfg.vocab, B, c->row_loss, loss, nullptr, nullptr, s, c->tc->dS_h,
                             c->tc->Vp, kGradScale));
     }
+    c->tc->defer_wgrad = false;   // phased backward: every bucket is complete when its call returns
     return tc_backward_head(c, p, g, s);
 }
 
 int tc_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int l, cudaStream_t s) {
     return tc_backward_layer(c, p, g, l, s);
 }
+
+bool tc_persistent_bwd(const zrb_ctx* c) { return c->tc && c->tc->bplan.ok; }
 
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries) {
     if (!c->tc || !c->tc->trace) { set_error("set ZRB_REC_TRACE=1 before creating the context"); return ZRB_E_STATE; }

@@ -58,11 +58,17 @@ struct GemmArgs {
     int splits;      // split-K factor (1 or 2); with 2 the epilogue adds atomically into a zeroed C
     float* sumsq_out; // or null: slot [tile * 8 + w] = sum of squares of the outputs epilogue warp w stored for `tile`
                       // (the wgrads feed clip_grad_norm_ from here instead of re-reading 200 MB of gradients)
+    float* C2;        // dual launch (or null): a second problem with the same A, shapes and pitches but its own B (tma_b2),
+    float* sumsq_out2;  // output and sum-of-squares slots; work items [num_tiles, 2*num_tiles) belong to it (splits == 1)
+    int pdl_tail;     // launched as a programmatic dependent of the kernel before it in the stream (it started while that
+                      // kernel was still running and consumes none of its outputs): wait for that kernel before exiting,
+                      // so that "this grid completed" keeps implying "everything before it in the stream completed"
 };
 
 template <bool A_MN, bool B_MN, int GBN, int MT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmArgs p) {
+gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const __grid_constant__ CUtensorMap tma_b2, GemmArgs p) {
     using Cfg = GemmCfg<GBN, MT>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kABytes = Cfg::kABytes;
@@ -85,12 +91,14 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n;
     const int num_kb = (p.K + GBK - 1) / GBK;
-    const int num_work = num_tiles * p.splits;            // work item w: tile = w % num_tiles, K range = w / num_tiles
-    const int kb_per = (num_kb + p.splits - 1) / p.splits;
+    const bool dual = p.C2 != nullptr;
+    const int num_work = dual ? 2 * num_tiles : num_tiles * p.splits;   // work item w: tile = w % num_tiles; w / num_tiles =
+    const int kb_per = (num_kb + p.splits - 1) / p.splits;              //   K range (split-K) or problem (dual launch)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if (dual) tma_prefetch_desc(&tma_b2);
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
         fence_mbar_init();
@@ -105,7 +113,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         // ===================== TMA producer =====================
         int s = 0; uint32_t ph = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-            const int tile = w % num_tiles, kb0 = (w / num_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+            const int tile = w % num_tiles, sp = dual ? 0 : w / num_tiles;
+            const int kb0 = sp * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+            const CUtensorMap* tmb = (dual && w >= num_tiles) ? &tma_b2 : &tma_b;
             const int m0 = (tile % p.tiles_m) * TM, n0 = (tile / p.tiles_m) * GBN;
             const int mt_n = (MT == 2 && m0 + GBM < p.M) ? 2 : 1;   // 128-row sub-tiles that hold real rows
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -122,11 +132,11 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     }
                 }
                 if (!B_MN) {
-                    tma_load_2d(b, &tma_b, &full[s], kb * GBK, n0);
+                    tma_load_2d(b, tmb, &full[s], kb * GBK, n0);
                 } else {
 #pragma unroll
                     for (int j = 0; j < GBN / 64; ++j)
-                        tma_load_2d(b + j * (GBK * 128), &tma_b, &full[s], n0 + 64 * j, kb * GBK);
+                        tma_load_2d(b + j * (GBK * 128), tmb, &full[s], n0 + 64 * j, kb * GBK);
                 }
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
@@ -139,7 +149,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         constexpr uint32_t idesc = make_idesc_f16(GBM, GBN, A_MN ? 1 : 0, B_MN ? 1 : 0);
         int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-            const int kb0 = (w / num_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+            const int kb0 = (dual ? 0 : w / num_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
             const int m0 = ((w % num_tiles) % p.tiles_m) * TM;
             const int mt_n = (MT == 2 && m0 + GBM < p.M) ? 2 : 1;
             mbar_wait(&acc_empty[as], aph ^ 1);
@@ -185,7 +195,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         float* sw = sEpi + ew * 32 * 33;
         int as = 0; uint32_t aph = 0;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-            const int tile = w % num_tiles, split = w / num_tiles;
+            const int tile = w % num_tiles, split = dual ? 0 : w / num_tiles;
+            float* const Cout = (dual && w >= num_tiles) ? p.C2 : p.C;
+            float* const ssq = (dual && w >= num_tiles) ? p.sumsq_out2 : p.sumsq_out;
             const int mt_n = (MT == 2 && (tile % p.tiles_m) * TM + GBM < p.M) ? 2 : 1;
             const int n0 = (tile / p.tiles_m) * GBN;
             const bool has_k = split * kb_per < num_kb;
@@ -213,7 +225,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 const float bv = (add_bias && col < p.N) ? p.bias[col] + (p.bias2 ? p.bias2[col] : 0.f) : 0.f;
                 const int rows = min(32, p.M - (m0 + q * 32));
                 if (col < p.N) {
-                    float* cptr = p.C + (int64_t)(m0 + q * 32) * p.ldc + col;
+                    float* cptr = Cout + (int64_t)(m0 + q * 32) * p.ldc + col;
                     if (p.splits > 1) {
                         if (rows == 32) {
 #pragma unroll
@@ -258,9 +270,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 if (!more_a) break;
                 cc += 4;
             }
-            if (p.sumsq_out) {
+            if (ssq) {
                 ss = warp_sum(ss);
-                if (lane == 0) p.sumsq_out[tile * 8 + ew] = ss;
+                if (lane == 0) ssq[tile * 8 + ew] = ss;
             }
             if (++as == kAccStages) { as = 0; aph ^= 1; }
         }
@@ -269,6 +281,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     __syncthreads();
     tcgen05_fence_after();
     if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (p.pdl_tail && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -332,7 +345,8 @@ int tc_make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
 }
 
 template <bool A_MN, bool B_MN, int GBN, int MT>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const GemmArgs& a,
+                       cudaStream_t s) {
     auto kern = gemm_f16_tc_kernel<A_MN, B_MN, GBN, MT>;
     const int idx = (A_MN ? 2 : 0) + (B_MN ? 1 : 0) + (GBN == 256 ? 4 : 0) + (MT == 2 ? 8 : 0);
     int dev = 0;
@@ -342,20 +356,35 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
         ZRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<GBN, MT>::kSmem));
         g_attr_set[dev][idx] = true;
     }
-    int grid = a.tiles_m * a.tiles_n * a.splits;
+    int grid = a.tiles_m * a.tiles_n * (a.C2 ? 2 : a.splits);
     if (grid > tc_num_sms()) grid = tc_num_sms();
-    kern<<<grid, kGemmThreads, GemmCfg<GBN, MT>::kSmem, s>>>(ta, tb, a);
+    if (a.pdl_tail) {
+        // programmatic dependent launch: the grid may start as soon as every CTA of the preceding kernel has executed
+        // griddepcontrol.launch_dependents (the persistent recurrence kernels do so once they are all resident), and
+        // fills the SMs that kernel leaves idle; CTAs that find no free SM start when it ends.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = GemmCfg<GBN, MT>::kSmem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ZRB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tb2, a));
+        count_launch();
+        return ZRB_OK;
+    }
+    kern<<<grid, kGemmThreads, GemmCfg<GBN, MT>::kSmem, s>>>(ta, tb, tb2, a);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
 
 template <int GBN, int MT>
-static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int a_mn, int b_mn,
-                         cudaStream_t s) {
-    if (!a_mn && !b_mn) return launch_gemm<false, false, GBN, MT>(ta, tb, a, s);
-    if (!a_mn && b_mn) return launch_gemm<false, true, GBN, MT>(ta, tb, a, s);
-    if (a_mn && !b_mn) return launch_gemm<true, false, GBN, MT>(ta, tb, a, s);
-    return launch_gemm<true, true, GBN, MT>(ta, tb, a, s);
+static int dispatch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const GemmArgs& a,
+                         int a_mn, int b_mn, cudaStream_t s) {
+    if (!a_mn && !b_mn) return launch_gemm<false, false, GBN, MT>(ta, tb, tb2, a, s);
+    if (!a_mn && b_mn) return launch_gemm<false, true, GBN, MT>(ta, tb, tb2, a, s);
+    if (a_mn && !b_mn) return launch_gemm<true, false, GBN, MT>(ta, tb, tb2, a, s);
+    return launch_gemm<true, true, GBN, MT>(ta, tb, tb2, a, s);
 }
 
 // Tile shape for an [M,N] output with K-block count num_kb: 128x256 when those tiles give every SM (nearly) a
@@ -402,29 +431,38 @@ int gemm_f16_tc_sumsq_slots(int M, int N, int K) {
 
 int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t ldb, int b_mn, float* C, int64_t ldc,
                 int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, float* sumsq_out,
-                const float* bias2) {
+                const float* bias2, bool pdl, const __half* B2, float* C2, float* sumsq_out2) {
     if (M <= 0 || N <= 0) return ZRB_OK;
+    ZRB_REQUIRE(!B2 == !C2, "dual launch needs both B2 and C2");
     ZRB_REQUIRE(!bias2 || bias, "bias2 needs bias");
     ZRB_REQUIRE(!sumsq_out || !accumulate, "sumsq_out needs a plain store epilogue");
     ZRB_REQUIRE(K > 0, "gemm_f16_tc needs K > 0");
-    const TileChoice tc = choose_tiles(M, N, cdiv(K, GBK), !sumsq_out && ldc == N);
+    const TileChoice tc = choose_tiles(M, N, cdiv(K, GBK), !sumsq_out && ldc == N && !C2);
     const int bn = tc.bn;
     CUtensorMap ta, tb;
     if (!a_mn) ZRB_TRY(tc_make_tmap_f16(&ta, A, K, M, lda, GBK, GBM, 1));
     else       ZRB_TRY(tc_make_tmap_f16(&ta, A, M, K, lda, 64, GBK, 1));
     if (!b_mn) ZRB_TRY(tc_make_tmap_f16(&tb, B, K, N, ldb, GBK, bn, 1));
     else       ZRB_TRY(tc_make_tmap_f16(&tb, B, N, K, ldb, 64, GBK, 1));
+    CUtensorMap tb2 = tb;
+    if (B2) {
+        if (!b_mn) ZRB_TRY(tc_make_tmap_f16(&tb2, B2, K, N, ldb, GBK, bn, 1));
+        else       ZRB_TRY(tc_make_tmap_f16(&tb2, B2, N, K, ldb, 64, GBK, 1));
+    }
     GemmArgs a;
     a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.bias = bias; a.C = C; a.ldc = ldc; a.accumulate = accumulate;
     a.tiles_m = tc.tiles_m; a.tiles_n = tc.tiles_n;
     a.splits = tc.splits;
     a.sumsq_out = sumsq_out;
     a.bias2 = bias2;
+    a.C2 = C2; a.sumsq_out2 = sumsq_out2;
+    a.pdl_tail = (pdl && a.splits == 1) ? 1 : 0;    // (a split launch is preceded by a memset: nothing to chain to)
     // split partials are added into a zeroed C: order-independent for two (a+b == b+a), last-bit run-to-run
     // differences beyond that
     if (a.splits > 1 && !accumulate) ZRB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));
-    if (tc.mt == 2) return dispatch_gemm<256, 2>(ta, tb, a, a_mn, b_mn, s);
-    return bn == 256 ? dispatch_gemm<256, 1>(ta, tb, a, a_mn, b_mn, s) : dispatch_gemm<128, 1>(ta, tb, a, a_mn, b_mn, s);
+    if (tc.mt == 2) return dispatch_gemm<256, 2>(ta, tb, tb2, a, a_mn, b_mn, s);
+    return bn == 256 ? dispatch_gemm<256, 1>(ta, tb, tb2, a, a_mn, b_mn, s)
+                     : dispatch_gemm<128, 1>(ta, tb, tb2, a, a_mn, b_mn, s);
 }
 
 }  // namespace zrb
@@ -434,5 +472,5 @@ extern "C" int zrb_gemm_f16(const void* A, int64_t lda, int32_t a_mn_major, cons
                             const float* bias, int32_t accumulate, void* stream) {
     ZRB_REQUIRE(A && B && C, "null argument");
     return zrb::gemm_f16_tc((const __half*)A, lda, a_mn_major, (const __half*)B, ldb, b_mn_major, C, ldc, M, N, K,
-                            alpha, bias, accumulate, (cudaStream_t)stream, nullptr, nullptr);
+                            alpha, bias, accumulate, (cudaStream_t)stream, nullptr, nullptr, false, nullptr, nullptr, nullptr);
 }

@@ -30,6 +30,10 @@ struct RecBwdArgs {
     const float* cst;         // [N,H]
     const float* c0;          // [B,H]
     __half* dG_h;             // [N,G4p] row-major, kGradScale * dG
+    float* db1;               // [4H] or null: bias gradient sum_{t,b} dG (model.py:35-36: b_ih and b_hh get the same
+    float* db2;               //      gradient), accumulated in registers over the window and reduced over the batch here
+    unsigned int* res_flag;   // or null: CTA 0 publishes res_value here when the whole grid is resident
+    unsigned int res_value;
     unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
     unsigned int base;
     int T, B, H, G4p, U, G, GB, Kc, nCTA;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive
+    if (threadIdx.x == 0) pdl_launch_dependents();
 
     if (warp == kRecLoadWarp && lane == 0) {
         // ===================== loader =====================
@@ -123,9 +128,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
         const int lbo_b = a.GB * 128;
+        const bool publish = a.res_flag != nullptr && blockIdx.x == 0;
+        if (publish && T == 1) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.res_flag), "r"(a.res_value) : "memory");
         for (int s = 1; s < T; ++s) {
             const int t = T - 1 - s;                      // step being computed; needs dG_{t+1}
             grid_counter_wait(a.counter, a.base + (unsigned int)s * a.nCTA);
+            if (publish && s == 1)   // every CTA arrived once: the whole grid is resident
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.res_flag), "r"(a.res_value) : "memory");
             if (tr) a.trace[s * 8 + 0] = clock64();
             fence_proxy_async_global();
             const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + rank) * b_bytes;
@@ -164,9 +173,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         // ===================== epilogue: 256 threads, cells (u, b) of this CTA's U units =====================
         const int tid = threadIdx.x;
         const int cells = a.U * B;                     // cell = b * U + u (u fastest: contiguous j)
-        float dcreg[kRecMaxCell];
+        float dcreg[kRecMaxCell], bsum[kRecMaxCell][4];
 #pragma unroll
-        for (int k = 0; k < kRecMaxCell; ++k) dcreg[k] = 0.f;
+        for (int k = 0; k < kRecMaxCell; ++k) {
+            dcreg[k] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bsum[k][q] = 0.f;
+        }
         const uint64_t n_total = (uint64_t)T * B * H;
         const uint32_t sD_addr = smem_u32(sD);
         uint32_t part_addr[4];
@@ -281,6 +294,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     float v = fminf(fmaxf(dg4[q] * kGradScale, -65504.f), 65504.f);
                     hv[k][q] = __float2half_rn(v);
                     img[(size_t)q * img_gate] = hv[k][q];
+                    bsum[k][q] += dg4[q];
                 }
             }
             if (tr && tid == 0) a.trace[s * 8 + 6] = clock64();
@@ -299,6 +313,29 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 __half* hrow = a.dG_h + ((size_t)t * B + b) * a.G4p + j0 + u;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) hrow[(size_t)q * H] = hv[k][q];
+            }
+        }
+        if (a.db1) {
+            // bias gradients: per-cell sums over the window -> shared memory (the operand buffer is idle now: the last
+            // MMAs were waited for before the last drain) -> fixed-order sum over the batch, one thread per (gate, unit)
+            float* sred = reinterpret_cast<float*>(sB);          // [4][B][U]
+#pragma unroll
+            for (int k = 0; k < kRecMaxCell; ++k) {
+                int cell = tid + kRecEpiThreads * k;
+                if (cell < cells) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sred[q * cells + cell] = bsum[k][q];
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < 4 * a.U) {
+                const int q = tid / a.U, u = tid % a.U;
+                if (u < nu) {
+                    float sacc = 0.f;
+                    for (int b = 0; b < B; ++b) sacc += sred[q * cells + b * a.U + u];
+                    a.db1[(size_t)q * H + j0 + u] = sacc;
+                    if (a.db2) a.db2[(size_t)q * H + j0 + u] = sacc;
+                }
             }
         }
     }
@@ -366,7 +403,8 @@ int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
 
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
                  const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
-                 int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace) {
+                 int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace, float* db1, float* db2,
+                 unsigned int* resident_flag, unsigned int resident_value) {
     static bool attr[64] = {};   // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
@@ -378,7 +416,7 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     RecBwdArgs a;
     a.base = counter_base;
     a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
-    a.counter = counter;
+    a.counter = counter; a.db1 = db1; a.db2 = db2; a.res_flag = resident_flag; a.res_value = resident_value;
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.nCTA);
@@ -391,16 +429,37 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     attrs[1].id = cudaLaunchAttributeCooperative;
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
-    // ZRB_NO_COOP=1: cluster launch without the cooperative attribute (profilers refuse the combination; the
-    // grid of <= 132 CTAs, one per SM, is co-resident on an otherwise idle device anyway)
-    static const bool no_coop = getenv("ZRB_NO_COOP") != nullptr;
+    // The grid barrier needs all nCTA CTAs co-resident.  The cooperative attribute makes the driver guarantee it (or
+    // refuse the launch).  Profilers (Nsight Compute) refuse the cooperative + cluster combination, so under a
+    // profiler -- detected through the injection environment it sets up, or forced with ZRB_NO_COOP=1 -- the kernel is
+    // launched as a plain cluster launch AFTER checking with the occupancy API that the whole grid fits the device
+    // (one CTA per SM, clusters of 4).  Without the guarantee, another context holding SMs (MPS, a concurrent
+    // kernel) could leave CTAs unscheduled; the barrier waits are bounded and trap after ~3 s instead of hanging.
+    static const bool no_coop = getenv("ZRB_NO_COOP") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                                getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                                getenv("NVTX_INJECTION64_PATH") != nullptr;
     cfg.numAttrs = no_coop ? 1 : 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
-    if (e != cudaSuccess) {
-        // some drivers refuse cooperative + cluster together: the grid (<= 132 CTAs, one per SM) is
-        // co-resident on an otherwise idle device anyway
-        (void)cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    if (!no_coop) {
+        e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+            (void)cudaGetLastError();
+            set_error("lstm_rec_bwd: the %d-CTA grid cannot be co-resident on this device (cooperative launch too large)",
+                      p.nCTA);
+            return ZRB_E_CUDA;
+        }
+        if (e != cudaSuccess) (void)cudaGetLastError();   // e.g. not supported under a tool: try the checked plain launch
+    }
+    if (no_coop || e != cudaSuccess) {
         cfg.numAttrs = 1;
+        int max_clusters = 0;
+        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_bwd_kernel, &cfg);
+        if (oe != cudaSuccess || max_clusters * 4 < p.nCTA) {
+            (void)cudaGetLastError();
+            set_error("lstm_rec_bwd: %d clusters of 4 needed, the device can hold %d at once (%s)", p.nCTA / 4,
+                      max_clusters, oe == cudaSuccess ? "grid would not be co-resident" : cudaGetErrorString(oe));
+            return ZRB_E_CUDA;
+        }
         e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
     }
     if (e != cudaSuccess) {

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
 
     if (warp == kRecLoadWarp && lane == 0) {
         // ===================== loader =====================

@@ -46,6 +46,11 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 }
 
 
+// Programmatic dependent launch: once EVERY CTA of this grid has executed this (i.e. the whole persistent grid is
+// resident), a kernel enqueued behind it with the programmatic-serialization attribute may start on the SMs this grid
+// leaves idle (148 - 125 / 128).  Kernels launched normally behind it are unaffected.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // sigmoid / tanh on the SFU exp path (abs error ~1e-7, far below the fp16 operand noise of this engine)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }

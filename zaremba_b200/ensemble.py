@@ -65,9 +65,12 @@ def gather_probs(local, n_models, group=None):
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return torch.stack([local[m] for m in range(n_models)])
-    n_tok = torch.tensor([0 if any_vec is None else any_vec.numel()], device=None if any_vec is None else any_vec.device)
+    if any_vec is not None:
+        dev = any_vec.device
+    else:   # a rank that hosts no model still joins the collectives: NCCL needs a CUDA tensor
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    n_tok = torch.tensor([0 if any_vec is None else any_vec.numel()], device=dev)
     dist.all_reduce(n_tok, op=dist.ReduceOp.MAX, group=group)
-    dev = any_vec.device if any_vec is not None else n_tok.device
     full = torch.zeros(n_models, int(n_tok.item()), device=dev, dtype=torch.float32)
     for m, v in local.items():
         full[m] = v

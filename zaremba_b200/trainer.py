@@ -39,8 +39,11 @@ def minibatch(data, batch_size, seq_length):
 
 class Trainer:
     def __init__(self, model: Model, batch_size: int, seq_length: int, process_group=None,
-                 keep_clipped_grads: bool = False):
-        """keep_clipped_grads: after a step `.grad` holds coef * g as clip_grad_norm_ (main.py:115) leaves it.  The
+                 keep_clipped_grads: bool = False, data_parallel: bool = True):
+        """data_parallel: when torch.distributed is initialised, shard the batch over the ranks and all-reduce the
+        gradients (default).  False = this process trains / evaluates its own replica alone (the sharded ensemble of
+        BASELINE configs[4]: one model per GPU, no gradient exchange).
+        keep_clipped_grads: after a step `.grad` holds coef * g as clip_grad_norm_ (main.py:115) leaves it.  The
         default skips that store (the values are dead: the next step overwrites them) and `.grad` keeps the raw
         gradients of the step; weights, loss and norm are the same either way."""
         if model.lstm_type != "pytorch":
@@ -51,7 +54,8 @@ class Trainer:
         self.model, self.B, self.T, self.dev = model, batch_size, seq_length, dev
         self.pg = process_group
         self._keep_clipped = bool(keep_clipped_grads)
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = (dist.get_world_size(process_group)
+                      if data_parallel and dist.is_available() and dist.is_initialized() else 1)
         params = model.ordered_parameters()
         sizes = [p.numel() for p in params]
         # one flat parameter buffer and one flat gradient buffer; the nn.Parameters become views
@@ -60,8 +64,13 @@ class Trainer:
         # "nccl" = one torch.distributed all_reduce after backward
         # measured on 8xB200 (profiles/r01_bench_dp*.json): ce wins at 2 and 4 ranks (1.97 vs 2.23 ms, 2.10 vs
         # 2.39 ms), NCCL/NVLS alone wins at 8 (2.41 vs 2.55 ms: seven small peer copies per phase)
+        #   "nccl_ov" = bucket all-reduces on a communicator limited to a few CTAs, each started once the backward
+        #               recurrence kernel that runs beside it is resident (zrb_resident_flag), tail + sparse embedding
+        #               rows on the full communicator
         default = "ce" if self.world <= 4 else "nccl"
         self.transport = os.environ.get("ZRB_DP_TRANSPORT", default) if self.world > 1 else None
+        if self.transport not in (None, "ce", "nccl", "nccl_ov"):
+            raise ValueError(f"unknown ZRB_DP_TRANSPORT {self.transport!r}")
         self._dp = None
         if self.transport == "ce" and not self._ce_supported():
             self.transport = "nccl"        # multi-node run or no P2P between the GPUs: one NCCL all-reduce instead
@@ -109,11 +118,26 @@ class Trainer:
         self.overlap = os.environ.get("ZRB_DP_OVERLAP", "0") == "1"
         self._ctx_cached = None
         _ = self.ctx
-        # single process: the fused step owns the gradient buffers -> touch only the window's embedding rows
-        self._embed_sparse = self.world == 1 and os.environ.get("ZRB_EMBED_SPARSE", "1") == "1"
-        _lib.check(_lib.load().zrb_set_embed_sparse(self.ctx, 1 if self._embed_sparse else 0))
+        # single process: the fused step owns the gradient buffers -> touch only the window's embedding rows and take
+        # the matrices' clip norm from the wgrad epilogues (mode 1).  Data parallel with the sparse embedding exchange
+        # ("ce", "nccl_ov"): rows-only embedding handling over ALL ranks' tokens (mode 2)
+        sparse_on = os.environ.get("ZRB_EMBED_SPARSE", "1") == "1"
+        self._embed_sparse = (1 if self.world == 1 else (2 if self.transport in ("ce", "nccl_ov") else 0)) if sparse_on else 0
+        _lib.check(_lib.load().zrb_set_embed_sparse(self.ctx, self._embed_sparse))
         _lib.check(_lib.load().zrb_set_keep_clipped_grads(self.ctx, 1 if self._keep_clipped else 0))
-        if self.transport == "ce":
+        self._pg_lo = None
+        if self.transport == "nccl_ov":
+            # a second communicator whose kernels take at most `ctas` SMs: they fit beside the 128-CTA backward
+            # recurrence (148 SMs) instead of evicting part of it (NCCL's default 24-32 channels do: rec_bwd 2x slower)
+            ctas = int(os.environ.get("ZRB_DP_NCCL_CTAS", "16"))
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = ctas
+            opts.config.min_ctas = min(ctas, 4)
+            self._pg_lo = dist.new_group(backend="nccl", pg_options=opts)
+            warm = torch.zeros(1 << 20, device=dev)
+            dist.all_reduce(warm, group=self._pg_lo)          # communicator set-up outside the timed steps
+            torch.cuda.synchronize(dev)
+        if self.transport in ("ce", "nccl_ov"):
             H, N = model.hidden_size, batch_size * seq_length
             self._rows = torch.zeros(N, H, device=dev)
             self._rows_all = torch.zeros(self.world * N, H, device=dev)
@@ -181,11 +205,7 @@ class Trainer:
         lo, hi = self._buckets[nb - 1]
         # tail: layer-0 gradients through one NCCL all-reduce (alone on the GPU); the embedding gradient as rows
         allreduce_sum_(self.flat_g[self._embed_end:hi], self.pg)
-        N = T * B
-        dist.all_gather_into_tensor(self._rows_all[: self.world * N], self._rows[:N], group=self.pg)
-        dist.all_gather_into_tensor(self._ids_all[: self.world * N], x.reshape(-1), group=self.pg)
-        _lib.check(lib.zrb_embed_scatter_rows(self.ctx, _lib.ptr(self.flat_g), _lib.ptr(self._ids_all),
-                                              _lib.ptr(self._rows_all), self.world * N, st))
+        self._exchange_embedding_rows(lib, x, T, B)
         _lib.check(lib.zrb_dp_finish_step(self._dp, st))
         _lib.check(lib.zrb_set_embed_rows_out(self.ctx, None))
 
@@ -196,7 +216,7 @@ class Trainer:
         c = self.model._context(self.T, self.B)
         if self._ctx_cached is None or c.value != self._ctx_cached:
             _lib.check(_lib.load().zrb_params_changed(c))
-            _lib.check(_lib.load().zrb_set_embed_sparse(c, 1 if getattr(self, "_embed_sparse", False) else 0))
+            _lib.check(_lib.load().zrb_set_embed_sparse(c, int(getattr(self, "_embed_sparse", 0))))
             _lib.check(_lib.load().zrb_set_keep_clipped_grads(c, 1 if self._keep_clipped else 0))
             self._ctx_cached = c.value
         return c
@@ -245,6 +265,8 @@ class Trainer:
         self._check_versions()
         if self.world > 1 and self.transport == "ce":
             self._grads_ce(lib, x, y, T, B)
+        elif self.world > 1 and self.transport == "nccl_ov":
+            self._grads_nccl_ov(lib, x, y, T, B)
         elif self.world > 1 and self.overlap:
             self._grads_overlapped(lib, x, y, T, B)
         else:
@@ -261,6 +283,54 @@ class Trainer:
                                              float(max_norm), _lib.ptr(self.norm), self._stream()))
         self.step += 1
         return self.loss, self.norm
+
+    def _exchange_embedding_rows(self, lib, x, T, B):
+        """Sparse form of the embedding gradient: all-gather every rank's N token ids and N masked gradient rows
+        (4 MB per rank instead of a 60 MB dense all-reduce) and scatter them deterministically into the dense buffer."""
+        N = T * B
+        dist.all_gather_into_tensor(self._rows_all[: self.world * N], self._rows[:N], group=self.pg)
+        dist.all_gather_into_tensor(self._ids_all[: self.world * N], x.reshape(-1), group=self.pg)
+        _lib.check(lib.zrb_embed_scatter_rows(self.ctx, _lib.ptr(self.flat_g), _lib.ptr(self._ids_all),
+                                              _lib.ptr(self._rows_all), self.world * N, self._stream()))
+
+    def _grads_nccl_ov(self, lib, x, y, T, B):
+        """Backward in phases; the buckets that finish early (fc, upper layers) are all-reduced on the few-CTA
+        communicator `_pg_lo` on a side stream.  Each of those all-reduces is held back (cuStreamWaitValue32 on the
+        flag the recurrence kernel publishes) until the backward recurrence launched right after the bucket completed
+        is fully resident, so NCCL's CTAs can only land on the SMs that kernel leaves idle.  The bucket that completes
+        with the end of backward (layer 0) and the embedding rows go through the full-width communicator."""
+        cur = torch.cuda.current_stream(self.dev)
+        comm = self._comm_stream
+        L = self.model.layer_num
+        flag, nxt = C.c_void_p(), C.c_uint32()
+
+        def reduce_bucket_gated(k):
+            lo, hi = self._buckets[k]
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            comm.wait_event(ev)
+            _lib.check(lib.zrb_resident_flag(self.ctx, C.byref(flag), C.byref(nxt)))
+            if nxt.value:
+                _lib.check(lib.zrb_stream_wait_value32(comm.cuda_stream, flag, nxt.value))
+            with torch.cuda.stream(comm):
+                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self._pg_lo)
+
+        _lib.check(lib.zrb_set_embed_rows_out(self.ctx, _lib.ptr(self._rows)))
+        _lib.check(lib.zrb_train_step_begin(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x), _lib.ptr(y),
+                                            T, B, C.byref(self._st), C.byref(self._st), self.seed, self.step,
+                                            _lib.ptr(self.loss), cur.cuda_stream))
+        reduce_bucket_gated(0)
+        k = 1
+        for l in range(L - 1, -1, -1):
+            _lib.check(lib.zrb_train_step_layer(self.ctx, C.byref(self._ps), C.byref(self._gs), l, cur.cuda_stream))
+            if l >= 1:
+                reduce_bucket_gated(k)
+                k += 1
+        lo, hi = self._buckets[-1]
+        allreduce_sum_(self.flat_g[self._embed_end:hi], self.pg)
+        self._exchange_embedding_rows(lib, x, T, B)
+        cur.wait_stream(comm)
+        _lib.check(lib.zrb_set_embed_rows_out(self.ctx, None))
 
     def _grads_overlapped(self, lib, x, y, T, B):
         """Backward in phases (zrb_train_step_begin / _layer); as soon as a bucket of the flat gradient
