@@ -204,6 +204,11 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
     return ZRB_OK;
 }
 
+static bool prof_keeps_pdl() {
+    static const bool on = getenv("ZRB_PROF_KEEP_PDL") != nullptr;
+    return on;
+}
+
 // next block of sum-of-squares slots for an [M,N] weight gradient, or null when the step does not fuse the norm
 static float* wgrad_sumsq(zrb_ctx* c, int M, int N, int K) {
     zrb_tc_state* t = c->tc;
@@ -240,7 +245,7 @@ static int tc_backward_head(zrb_ctx* c, const zrb_params* p, const zrb_params* g
         // dW[V,H] = dS^T[V,N] * A[N,H]     (both operands MN-major: contraction over tokens).  Nothing downstream in
         // backward reads it: with deferral on it runs underneath the first backward recurrence instead of before it.
         t->pending = 0;
-        if (t->defer_wgrad && t->bplan.ok && !c->prof_on) t->pending = 1;
+        if (t->defer_wgrad && t->bplan.ok && (!c->prof_on || prof_keeps_pdl())) t->pending = 1;
         else ZRB_TRY(gemm_f16_tc(t->dS_h, Vp, 1, t->x_h[L], Hp, 1, g->fc_w, H, V, H, N, inv, nullptr, 0, s,
                                  wgrad_sumsq(c, V, H, N)));
     }
@@ -264,13 +269,13 @@ static int tc_issue_pending(zrb_ctx* c, const zrb_params* g, cudaStream_t s) {
     const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab, N = c->T * c->B;
     const int kind = t->pending;
     t->pending = 0;
+    // (no event bracket here: an event record between the recurrence kernel and its programmatic dependent would sit
+    // between the two launches; while profiling with ZRB_PROF_KEEP_PDL=1 the time lands in the enclosing REC_BWD class)
     if (kind == 1) {
-        ProfScope ps(c, ZRB_PROF_PROJ_BWD, s);
         return gemm_f16_tc(t->dS_h, t->Vp, 1, t->x_h[L], t->Hp, 1, g->fc_w, H, V, H, N, 1.f / kGradScale, nullptr, 0, s,
                            wgrad_sumsq(c, V, H, N), nullptr, true);
     }
     if (kind == 2) {
-        ProfScope ps(c, ZRB_PROF_GEMM_WGRAD, s);
         const int l = t->pending_layer;
         return tc_layer_wgrads(c, g, l, (l & 1) ? t->dG_h_alt : t->dG_h, true, s);
     }
@@ -304,7 +309,7 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
             ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], dG_h,
                                  t->counter + 32, t->cnt_b, T, B, H, G4p, m, s,
                                  t->trace ? t->trace + (size_t)c->cfg.max_seq * 8 : nullptr, g->b_ih[l], g->b_hh[l],
-                                 c->resident_flag, ++c->resident_seq));
+                                 c->resident_flag, ++c->resident_seq, c->dG /* [N,4H] fp32, idle on this path */));
             t->cnt_b += arrivals;
             ZRB_TRY(tc_issue_pending(c, g, s));   // runs on the SMs the cluster kernel leaves idle
         } else {
@@ -327,7 +332,7 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
         }
         // dW_ih, dW_hh: nothing downstream in backward reads them -> for l > 0 they run underneath the next layer's
         // recurrence (which writes the other dG buffer); the bias gradients come out of the recurrence kernel itself
-        if (t->defer_wgrad && t->bplan.ok && l > 0 && !c->prof_on) {
+        if (t->defer_wgrad && t->bplan.ok && l > 0 && (!c->prof_on || prof_keeps_pdl())) {
             t->pending = 2;
             t->pending_layer = l;
         } else {

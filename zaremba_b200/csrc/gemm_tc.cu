@@ -361,7 +361,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     if (a.pdl_tail) {
         // programmatic dependent launch: the grid may start as soon as every CTA of the preceding kernel has executed
         // griddepcontrol.launch_dependents (the persistent recurrence kernels do so once they are all resident), and
-        // fills the SMs that kernel leaves idle; CTAs that find no free SM start when it ends.
+        // fills the SMs that kernel leaves idle; CTAs that find no free SM start when it ends.  ONE work item per CTA
+        // here (not the persistent one-CTA-per-SM grid): the hardware block scheduler then hands tiles to whichever
+        // SMs are free, so the ~20 idle SMs work through most of the tiles while the recurrence runs, instead of each
+        // late CTA still owning a full static share of them.
+        grid = a.tiles_m * a.tiles_n * (a.C2 ? 2 : a.splits);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads);
         cfg.dynamicSmemBytes = GemmCfg<GBN, MT>::kSmem; cfg.stream = s;

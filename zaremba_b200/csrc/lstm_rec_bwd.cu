@@ -32,6 +32,7 @@ struct RecBwdArgs {
     __half* dG_h;             // [N,G4p] row-major, kGradScale * dG
     float* db1;               // [4H] or null: bias gradient sum_{t,b} dG (model.py:35-36: b_ih and b_hh get the same
     float* db2;               //      gradient), accumulated in registers over the window and reduced over the batch here
+    float* db_scratch;        // [4][B][H] fp32 scratch of that reduction (needed when db1 is set)
     unsigned int* res_flag;   // or null: CTA 0 publishes res_value here when the whole grid is resident
     unsigned int res_value;
     unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
@@ -316,23 +317,25 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             }
         }
         if (a.db1) {
-            // bias gradients: per-cell sums over the window -> shared memory (the operand buffer is idle now: the last
-            // MMAs were waited for before the last drain) -> fixed-order sum over the batch, one thread per (gate, unit)
-            float* sred = reinterpret_cast<float*>(sB);          // [4][B][U]
+            // bias gradients: per-cell sums over the window -> a global scratch [4][B][H] (no shared-memory region of
+            // a guaranteed size is free: peers may still read the staging buffer) -> fixed-order sum over the batch by
+            // one thread per (gate, unit) of this CTA.  bar.sync orders the CTA's own global writes for its readers.
 #pragma unroll
             for (int k = 0; k < kRecMaxCell; ++k) {
                 int cell = tid + kRecEpiThreads * k;
-                if (cell < cells) {
+                int b = cell / a.U, u = cell % a.U;
+                if (cell < cells && u < nu) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) sred[q * cells + cell] = bsum[k][q];
+                    for (int q = 0; q < 4; ++q) a.db_scratch[((size_t)q * B + b) * H + j0 + u] = bsum[k][q];
                 }
             }
+            __threadfence_block();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid < 4 * a.U) {
                 const int q = tid / a.U, u = tid % a.U;
                 if (u < nu) {
                     float sacc = 0.f;
-                    for (int b = 0; b < B; ++b) sacc += sred[q * cells + b * a.U + u];
+                    for (int b = 0; b < B; ++b) sacc += a.db_scratch[((size_t)q * B + b) * H + j0 + u];
                     a.db1[(size_t)q * H + j0 + u] = sacc;
                     if (a.db2) a.db2[(size_t)q * H + j0 + u] = sacc;
                 }
@@ -404,7 +407,8 @@ int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
                  const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
                  int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace, float* db1, float* db2,
-                 unsigned int* resident_flag, unsigned int resident_value) {
+                 unsigned int* resident_flag, unsigned int resident_value, float* db_scratch) {
+    ZRB_REQUIRE(!db1 || db_scratch, "bias gradients need the scratch buffer");
     static bool attr[64] = {};   // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
@@ -416,7 +420,7 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     RecBwdArgs a;
     a.base = counter_base;
     a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
-    a.counter = counter; a.db1 = db1; a.db2 = db2; a.res_flag = resident_flag; a.res_value = resident_value;
+    a.counter = counter; a.db1 = db1; a.db2 = db2; a.db_scratch = db_scratch; a.res_flag = resident_flag; a.res_value = resident_value;
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.nCTA);

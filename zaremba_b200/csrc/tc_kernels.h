@@ -65,7 +65,7 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
                  const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
                  int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace = nullptr, float* db1 = nullptr,
                  float* db2 = nullptr,    // db1 / db2: bias gradients sum_{t,b} dG [4H] written by the kernel (or null)
-                 unsigned int* resident_flag = nullptr, unsigned int resident_value = 0);
+                 unsigned int* resident_flag = nullptr, unsigned int resident_value = 0, float* db_scratch = nullptr);
 // resident_flag: CTA 0 stores resident_value there once every CTA of the grid has arrived at the first grid barrier,
 // i.e. the whole persistent grid holds its SMs: a stream gated on it (cuStreamWaitValue32) can then start work that
 // must only take the SMs this kernel leaves free (the data-parallel bucket all-reduce).
