@@ -1,5 +1,6 @@
 """Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the CUDA data-parallel step through BOTH gradient
-transports (`ce` = copy engines over NVLink peer memory, `nccl` = one all-reduce) against a single process at batch
+transports (`ce` = copy engines over NVLink peer memory, `nccl` = one all-reduce, `nccl_ov` = bucket all-reduces on a
+few-CTA communicator gated on the backward recurrence's residency flag) against a single process at batch
 2B, with dropout ON, and the sharded ensemble (one model per rank) against the reference fixture.
 
 Semantics under test: rows of the global batch are independent streams (main.py:63-66), the loss is
@@ -113,7 +114,7 @@ def _dp_worker(rank, world, port, q, transport):
     q.put((rank, res))
 
 
-@pytest.mark.parametrize("transport", ["ce", "nccl"])
+@pytest.mark.parametrize("transport", ["ce", "nccl", "nccl_ov"])
 def test_dp_step_equals_single_process_with_dropout(transport):
     _need_two()
     out = _spawn(_dp_worker, 2, transport)

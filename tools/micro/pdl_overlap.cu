@@ -34,7 +34,7 @@ __global__ void secondary(unsigned long long* starts, unsigned long long work_ns
         unsigned long long t0 = gtime();
         starts[blockIdx.x] = t0;
         while (gtime() - t0 < work_ns) {}
-        if (tail_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (tail_wait == 1 || (tail_wait == 2 && blockIdx.x == 0)) asm volatile("griddepcontrol.wait;" ::: "memory");
     }
     __syncthreads();
 }
@@ -47,10 +47,14 @@ int main() {
     CK(cudaFuncSetAttribute(secondary, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     unsigned long long *stamps, *starts, h_stamps[2], h_starts[nsec];
     CK(cudaMalloc(&stamps, 16)); CK(cudaMalloc(&starts, nsec * 8));
-    cudaStream_t s; CK(cudaStreamCreate(&s));
+    cudaStream_t s_created; CK(cudaStreamCreate(&s_created));
     const char* names[] = {"plain", "cooperative", "cluster4", "cluster4+cooperative"};
+    for (int which_stream = 0; which_stream < 3; ++which_stream)
     for (int trigger = 1; trigger >= 0; --trigger)
     for (int flavour = 0; flavour < 4; ++flavour) {
+        if (which_stream >= 1) { if (trigger == 0 || (flavour != 0 && flavour != 3)) continue; }
+        const int tail_mode = which_stream == 2 ? 2 : 1;   // 2: only CTA 0 of the dependent grid waits for the primary
+        cudaStream_t s = which_stream == 0 ? s_created : (cudaStream_t)0;   // 1: the legacy default stream
         for (int rep = 0; rep < 2; ++rep) {
             CK(cudaMemsetAsync(starts, 0, nsec * 8, s));
             cudaLaunchConfig_t cfg = {};
@@ -65,7 +69,7 @@ int main() {
             cudaLaunchAttribute a2[1];
             a2[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; a2[0].val.programmaticStreamSerializationAllowed = 1;
             c2.attrs = a2; c2.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&c2, secondary, starts, 20000ull, 1));
+            CK(cudaLaunchKernelEx(&c2, secondary, starts, 20000ull, tail_mode));
             CK(cudaStreamSynchronize(s));
             CK(cudaMemcpy(h_stamps, stamps, 16, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(h_starts, starts, nsec * 8, cudaMemcpyDeviceToHost));
@@ -76,8 +80,8 @@ int main() {
                 if (d < first) first = d;
             }
             if (rep == 1)
-                printf("primary %-22s trigger=%d: primary ran %.1f us; %3d of %d dependent CTAs started before it ended; first dependent CTA at +%.1f us\n",
-                       names[flavour], trigger, (h_stamps[1] - h_stamps[0]) / 1e3, early, nsec, first / 1e3);
+                printf("%s primary %-22s trigger=%d: primary ran %.1f us; %3d of %d dependent CTAs started before it ended; first dependent CTA at +%.1f us\n",
+                       which_stream == 2 ? "[legacy stream, only CTA 0 waits]" : which_stream ? "[legacy default stream]" : "[created stream]", names[flavour], trigger, (h_stamps[1] - h_stamps[0]) / 1e3, early, nsec, first / 1e3);
         }
     }
     return 0;

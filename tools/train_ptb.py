@@ -146,6 +146,14 @@ for epoch in range(n_epochs):
     e_words = [0]
 
     def log(i, loss, norm, epoch=epoch):
+        if loss != loss:                               # NaN: the run is dead, do not burn the remaining epochs
+            if rank == 0:
+                print(f"NON-FINITE train loss at epoch {epoch + 1}, batch {i}: aborting (seed {args.seed})", flush=True)
+                if args.json:
+                    json.dump({"impl": args.impl, "recipe": args.recipe, "seed": args.seed, "diverged": True,
+                               "epoch": epoch + 1, "batch": i, "valid_ppl_per_epoch": [round(v, 3) for v in val_curve]},
+                              open(args.json, "w"), indent=1)
+            sys.exit(3)
         if rank == 0:
             toc = timeit.default_timer()
             seen = words_seen + (i + 1) * T * B * world

@@ -281,7 +281,10 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     __syncthreads();
     tcgen05_fence_after();
     if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-    if (p.pdl_tail && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ONE CTA keeps the grid from completing before the primary has: a CTA blocked here holds its SM, and if every
+    // CTA waited, the ~20 SMs the recurrence leaves idle would each run a single tile and then sit until it ends
+    // (measured: tools/micro/pdl_overlap.cu, 20 of 148 dependent CTAs ran during the primary)
+    if (p.pdl_tail && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---- host side ----------------------------------------------------------------------------------

@@ -33,6 +33,8 @@ struct RecBwdArgs {
     float* db1;               // [4H] or null: bias gradient sum_{t,b} dG (model.py:35-36: b_ih and b_hh get the same
     float* db2;               //      gradient), accumulated in registers over the window and reduced over the batch here
     float* db_scratch;        // [4][B][H] fp32 scratch of that reduction (needed when db1 is set)
+    int push;                 // exchange of the cluster's partial products: 1 = st.async pushes into the owners' shared
+                              // memory (complete_tx on their mbarrier), 0 = stage + remote arrive + DSMEM pulls
     unsigned int* res_flag;   // or null: CTA 0 publishes res_value here when the whole grid is resident
     unsigned int res_value;
     unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
@@ -59,6 +61,12 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
 }
 __device__ __forceinline__ void st_dsmem_f32(uint32_t cluster_addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+// 16 bytes into a peer CTA's shared memory; the bytes are counted on that CTA's mbarrier (complete_tx), so the
+// reader needs no fence: observing the phase completion makes them visible
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -93,7 +101,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     uint64_t* bar_b = bars + 1;                    // [kRecPieces]
     uint64_t* bar_mma = bars + 1 + kRecPieces;
     uint64_t* bar_part = bar_mma + 1;              // 4 arrivals per step: every CTA of the cluster staged its partial
-    uint32_t* tmem_slot = (uint32_t*)(bar_part + 1);
+    uint64_t* bar_recv = bar_part + 1;             // push mode: all four CTAs' partials of this CTA's units have landed
+    uint32_t* tmem_slot = (uint32_t*)(bar_recv + 1);
+    // push mode reuses the staging buffer as the receive buffer sR[source rank][unit][batch (pitch ldr, 16-byte rows)]
+    const int ldr = Bp + 4;
+    float* sR = sD;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         for (int i = 0; i < kRecPieces; ++i) mbar_init(&bar_b[i], 1);
         mbar_init(bar_mma, kRecMmaWarps);
         mbar_init(bar_part, 4);
+        mbar_init(bar_recv, 1);
         fence_mbar_init();
     }
     if (warp == kRecMmaWarp) tmem_alloc<kRecTmemCols>(tmem_slot);
@@ -187,6 +200,8 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) part_addr[rr] = mapa_shared(sD_addr, rr);
         const uint32_t bar_part_addr = smem_u32(bar_part);
+        const uint32_t sR_addr = smem_u32(sR), bar_recv_addr = smem_u32(bar_recv);
+        const uint32_t recv_bytes = 4u * (uint32_t)a.U * (uint32_t)Bp * 4u;   // 4 sources x U units x Bp columns
         const float inv = 1.f / kGradScale;
         const size_t img_gate = (size_t)a.Kc * a.GB * 64;
 
@@ -213,6 +228,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 }
             }
             if (s > 0) {
+                if (a.push && tid == 0) mbar_expect_tx(bar_recv, recv_bytes);
                 bounded_mbar_wait(bar_mma, (s - 1) & 1);
                 tcgen05_fence_after();
                 if (tr && tid == 0) a.trace[s * 8 + 3] = clock64();
@@ -238,25 +254,40 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                                 for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(v[ai][i]);
                             }
                         if (lane < 16) {
-                            float* dst = sD + (16 * quad + lane) * ldd + c0;
+                            const int row = 16 * quad + lane;               // cluster-local unit of this accumulator row
+                            if (!a.push) {
+                                float* dst = sD + row * ldd + c0;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) dst[i] = acc[i];
+                                for (int i = 0; i < 8; ++i) dst[i] = acc[i];
+                            } else if (row < UC) {
+                                // straight from the registers into the shared memory of the CTA that owns this unit
+                                const int owner = row / a.U, uo = row - owner * a.U;
+                                const uint32_t dst = mapa_shared(sR_addr + (uint32_t)((((int)rank * a.U + uo) * ldr + c0) * 4), owner);
+                                const uint32_t rbar = mapa_shared(bar_recv_addr, owner);
+                                st_async_v4(dst, acc[0], acc[1], acc[2], acc[3], rbar);
+                                st_async_v4(dst + 16, acc[4], acc[5], acc[6], acc[7], rbar);
+                            }
                         }
                     }
                 }
                 tcgen05_fence_before();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
-                if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
-                {   // wait until all four CTAs of the cluster staged their partials
-                    uint32_t n = 0; long long t0 = 0;
-                    while (!mbar_try_wait_acq_cluster(bar_part, (s - 1) & 1)) {
-                        if ((++n & 0xFFFu) == 0) {
-                            long long now = clock64();
-                            if (t0 == 0) t0 = now;
-                            else if (now - t0 > kSpinCycles) asm volatile("trap;");
+                if (!a.push) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
+                    if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
+                    {   // wait until all four CTAs of the cluster staged their partials
+                        uint32_t n = 0; long long t0 = 0;
+                        while (!mbar_try_wait_acq_cluster(bar_part, (s - 1) & 1)) {
+                            if ((++n & 0xFFFu) == 0) {
+                                long long now = clock64();
+                                if (t0 == 0) t0 = now;
+                                else if (now - t0 > kSpinCycles) asm volatile("trap;");
+                            }
                         }
                     }
+                } else {
+                    if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
+                    bounded_mbar_wait(bar_recv, (s - 1) & 1);   // all 4 x U x Bp partial sums of my units have landed
                 }
             }
             if (tr && tid == 0) a.trace[s * 8 + 5] = clock64();
@@ -269,10 +300,15 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 if (!ok) continue;
                 float dh = dyv[k];
                 if (s > 0) {
-                    const uint32_t off = (uint32_t)(((int)rank * a.U + u) * ldd + b) * 4u;
-                    float pp[4];   // issue all four DSMEM loads before the first use (each is ~200+ clk)
+                    float pp[4];
+                    if (!a.push) {
+                        const uint32_t off = (uint32_t)(((int)rank * a.U + u) * ldd + b) * 4u;
+#pragma unroll             // issue all four DSMEM loads before the first use (each is ~200+ clk)
+                        for (int rr = 0; rr < 4; ++rr) pp[rr] = ld_dsmem_f32(part_addr[rr] + off);
+                    } else {
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) pp[rr] = ld_dsmem_f32(part_addr[rr] + off);
+                        for (int rr = 0; rr < 4; ++rr) pp[rr] = sR[(rr * a.U + u) * ldr + b];
+                    }
                     float r = (pp[0] + pp[1]) + (pp[2] + pp[3]);
                     dh += r * inv;
                 }
@@ -420,6 +456,8 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     RecBwdArgs a;
     a.base = counter_base;
     a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
+    static const bool pull = getenv("ZRB_BWD_PULL") != nullptr;   // A/B switch: the r01 staging + DSMEM-pull exchange
+    a.push = pull ? 0 : 1;
     a.counter = counter; a.db1 = db1; a.db2 = db2; a.db_scratch = db_scratch; a.res_flag = resident_flag; a.res_value = resident_value;
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     cudaLaunchConfig_t cfg = {};
