@@ -174,6 +174,16 @@ int  zrb_set_embed_sparse(zrb_ctx* ctx, int32_t on);
  * dead values -- main.py:109 zeroes them before the next use -- and storing them is 4 of the ~16 bytes per
  * parameter the update moves).  zrb_clip_sgd always stores them. */
 int  zrb_set_keep_clipped_grads(zrb_ctx* ctx, int32_t on);
+/* Lazy update (opt-in, tensor-core engine with the persistent recurrence kernels).  The SGD update of main.py:116-117 is
+ * HBM-bound work with no consumer until the next forward reaches the layer it belongs to.  With on = 1,
+ * zrb_train_step_update applies the clip norm, the embedding, layer 0 and all biases at once and DEFERS the matrices of
+ * layers >= 1 and fc.W: the next fused train step launches them as programmatic dependents of its forward recurrence
+ * kernels (layer l+1's update beside layer l's recurrence, fc.W's beside the last), on the ~23 SMs those leave idle.
+ * Every other entry point that reads parameters (zrb_forward, zrb_eval_step, zrb_clip_sgd, a second _update) applies
+ * what is pending first, so results never change -- but the CALLER's own reads of those parameter buffers between two
+ * steps must be preceded by zrb_flush_updates(ctx, stream).  Same arithmetic, same order per element. */
+int  zrb_set_lazy_update(zrb_ctx* ctx, int32_t on);
+int  zrb_flush_updates(zrb_ctx* ctx, void* stream);
 int  zrb_embed_scatter_rows(zrb_ctx* ctx, float* grad_embed, const int64_t* ids, const float* rows,
                             int64_t n_rows, void* stream);
 int  zrb_train_step_update(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,
@@ -204,6 +214,9 @@ int    zrb_dp_finish_step(zrb_dp* dp, void* stream);
  * number into a device flag once every CTA of its grid is resident.  zrb_resident_flag returns the flag and the value
  * the NEXT backward-recurrence launch of this context will publish (0: this context does not use the persistent
  * kernel, do not wait); zrb_stream_wait_value32 makes `stream` wait until *d_flag >= value (cuStreamWaitValue32). */
+/* CAUTION: a stream blocked in cuStreamWaitValue32 on a value that a kernel enqueued LATER on another stream of the same
+ * process will write can deadlock when the two streams share a hardware work queue (observed: a 2-GPU run hung).  Use the
+ * flag only from a stream that provably does not alias the launching stream's queue, or poll it from a kernel. */
 int  zrb_resident_flag(zrb_ctx* ctx, uint32_t** d_flag, uint32_t* next_value);
 int  zrb_stream_wait_value32(void* stream, const uint32_t* d_flag, uint32_t value);
 

@@ -1,6 +1,5 @@
 """Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the CUDA data-parallel step through BOTH gradient
-transports (`ce` = copy engines over NVLink peer memory, `nccl` = one all-reduce, `nccl_ov` = bucket all-reduces on a
-few-CTA communicator gated on the backward recurrence's residency flag) against a single process at batch
+transports (`ce` = copy engines over NVLink peer memory, `nccl` = one all-reduce) against a single process at batch
 2B, with dropout ON, and the sharded ensemble (one model per rank) against the reference fixture.
 
 Semantics under test: rows of the global batch are independent streams (main.py:63-66), the loss is
@@ -30,20 +29,33 @@ def _need_two():
         pytest.skip("needs 2 GPUs")
 
 
+def _guarded(fn, rank, world, port, q, *args):
+    """Worker entry: an exception in a rank is reported through the queue instead of leaving the parent to time out."""
+    try:
+        fn(rank, world, port, q, *args)
+    except BaseException as e:           # noqa: BLE001 -- report everything, the parent re-raises
+        import traceback
+        q.put((rank, {"error": "".join(traceback.format_exception(type(e), e, e.__traceback__))[-3000:]}))
+
+
 def _spawn(fn, world, *args):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + os.getpid() % 200
-    procs = [ctx.Process(target=fn, args=(r, world, port, q) + args) for r in range(world)]
+    procs = [ctx.Process(target=_guarded, args=(fn, r, world, port, q) + args) for r in range(world)]
     for p in procs:
         p.start()
     out = {}
-    for _ in range(world):
-        r, res = q.get(timeout=600)
-        out[r] = res
-    for p in procs:
-        p.join(60)
-        assert p.exitcode == 0
+    try:
+        for _ in range(world):
+            r, res = q.get(timeout=150)
+            out[r] = res
+            assert "error" not in res, f"rank {r}: {res['error']}"
+    finally:
+        for p in procs:
+            p.join(5 if len(out) < world else 60)
+            if p.is_alive():
+                p.kill()                 # exactly the processes this test started
     return out
 
 
@@ -70,7 +82,7 @@ def _dp_worker(rank, world, port, q, transport):
         x = data[rows, i * T:(i + 1) * T].t().contiguous().to(dev)
         y = data[rows, i * T + 1:(i + 1) * T + 1].t().contiguous().to(dev)
         seeds.append((tr.seed, tr.step))
-        loss, norm = tr.train_step(x, y, 1.0, 0.5)
+        loss, norm = tr.train_step(x, y, 1.0, 0.25)
         out.append((loss.item(), norm.item()))
     dp_p = tr.flat_p.clone()
     # replicas identical?
@@ -104,7 +116,7 @@ def _dp_worker(rank, world, port, q, transport):
             full = [torch.cat([allm[r][i, site].view(T, B, H) for r in range(world)], dim=1).contiguous()
                     for site in range(L + 1)]
             m2.set_explicit_dropout_masks(full)
-            loss, norm = tr2.train_step(x, y, 1.0, 0.5)
+            loss, norm = tr2.train_step(x, y, 1.0, 0.25)
             ref.append((loss.item(), norm.item()))
         scale = tr2.flat_p.abs().max().item()
         res.update(err=(dp_p - tr2.flat_p).abs().max().item() / scale, ref=ref, different_masks=different_masks)
@@ -114,17 +126,18 @@ def _dp_worker(rank, world, port, q, transport):
     q.put((rank, res))
 
 
-@pytest.mark.parametrize("transport", ["ce", "nccl", "nccl_ov"])
+@pytest.mark.parametrize("transport", ["ce", "nccl"])
 def test_dp_step_equals_single_process_with_dropout(transport):
     _need_two()
     out = _spawn(_dp_worker, 2, transport)
     r0 = out[0]
+    print("DP", transport, r0)
     assert out[0]["identical"] and out[1]["identical"], "replicas diverged across ranks"
     assert r0["different_masks"], "ranks must not share dropout masks"
     assert r0["err"] < 2e-3, r0
     for (l_ref, n_ref), l_dp, n_dp in zip(r0["ref"], r0["loss_sum"], r0["norms"]):
         assert abs(l_dp - l_ref) < 2e-3 * abs(l_ref) and abs(n_dp - n_ref) < 3e-3 * n_ref, r0
-    assert r0["norms"][0] > 0.5 * 1.5, "the clip should be active in this test"
+    assert r0["norms"][0] > 0.25, "the clip (max_norm 0.25) should be active in this test"
 
 
 def _ens_worker(rank, world, port, q):

@@ -177,6 +177,41 @@ def test_keep_clipped_grads_option(engine):
     assert (g0 - g1).abs().max().item() > 0.1 * scale, "default leaves the raw gradients"
 
 
+def test_lazy_update_equals_strict_update():
+    """Trainer(lazy_update=True) defers the upper-layer / fc weight updates to run beside the next step's forward
+    recurrences: after flush() the parameters must equal the strict schedule's (same arithmetic per element), eval in
+    between must see the updated weights without an explicit flush, and an un-flushed read shows what the docstring
+    says (fc.W still holding the previous step's values)."""
+    import zaremba_b200
+    c = StepCase("mid_H72")
+    res = {}
+    for lazy in (False, True):
+        m = _model_from_case(c, "tc")
+        m.train()
+        tr = zaremba_b200.Trainer(m, c.B, c.T, lazy_update=lazy)
+        x = torch.tensor(c.x(0)).to(_dev()).contiguous()
+        y = torch.tensor(c.y(0)).to(_dev()).contiguous()
+        fc_before = m.fc.W.detach().clone()
+        losses = []
+        for s in range(3):
+            loss, norm = tr.train_step(x, y, c.lr, 0.5 * c.norm(0))
+            losses.append(loss.item())
+            if s == 0 and lazy:
+                torch.cuda.synchronize()
+                assert torch.equal(m.fc.W.detach(), fc_before), "fc.W update should still be pending"
+            if s == 1:
+                m.eval()
+                ev = tr.eval_step(x, y).item()          # applies what is pending first
+                m.train()
+        tr.flush()
+        torch.cuda.synchronize()
+        res[lazy] = (losses, ev, tr.flat_p.clone())
+    for a, b in zip(res[False][0], res[True][0]):
+        assert abs(a - b) <= 1e-6 * abs(a), (res[False][0], res[True][0])
+    assert abs(res[False][1] - res[True][1]) <= 1e-6 * abs(res[False][1])
+    torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_host_buffer_step_equals_device_step(engine):
     """zrb_train_step_host (H2D/D2H inside) == device-token step, bit for bit in eval of loss."""

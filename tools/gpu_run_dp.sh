@@ -5,14 +5,14 @@ mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
   timeout 900 python -m pytest tests/test_gpu_multi.py -q > gpurun_out/pytest_multi.log 2>&1; echo "pytest multi rc=$?" >> gpurun_out/pytest_multi.log; tail -8 gpurun_out/pytest_multi.log
 fi
-for tr in ce nccl nccl_ov; do
+for tr in ce nccl; do
   ZRB_DP_TRANSPORT=$tr timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
      bench.py --gpus $N --steps $STEPS --warmup 10 --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_dp${N}_$tr.json 2> gpurun_out/bench_dp${N}_$tr.err
   echo "dp$N $tr rc=$?"; tail -2 gpurun_out/bench_dp${N}_$tr.err | cut -c1-300
 done
 python - <<PY
 import json
-for tr in ("ce","nccl","nccl_ov"):
+for tr in ("ce","nccl"):
     try:
         d=json.load(open("gpurun_out/bench_dp${N}_%s.json" % tr))
         print(tr, "ms/step", round(d["ms_per_step"],4), "tok/s", round(d["value"]), "e2e ms", round(d["e2e"]["ms_per_step"],4), d.get("dp_check"), d["roofline"]["class_ms_per_step"])

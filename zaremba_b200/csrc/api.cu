@@ -149,6 +149,18 @@ int zrb_params_changed(zrb_ctx* c) {
     return ZRB_OK;
 }
 
+int zrb_set_lazy_update(zrb_ctx* c, int32_t on) {
+    ZRB_REQUIRE(c, "null ctx");
+    c->lazy_update = on != 0;
+    return ZRB_OK;
+}
+
+int zrb_flush_updates(zrb_ctx* c, void* stream) {
+    ZRB_REQUIRE(c, "null ctx");
+    if (c->cfg.engine != ZRB_ENGINE_TC) return ZRB_OK;
+    return tc_flush_updates(c, (cudaStream_t)stream);
+}
+
 int zrb_dropout_mask(uint64_t seed, uint64_t step, int32_t site, int64_t n, float p, uint8_t* mask_out,
                      void* stream) {
     ZRB_REQUIRE(mask_out && n >= 0, "bad args");
@@ -201,6 +213,7 @@ int zrb_clip_sgd(zrb_ctx* c, int32_t n, float* const* params, float* const* grad
                  float max_norm, float* norm_out, void* stream) {
     ZRB_REQUIRE(c && params && grads && sizes, "null argument");
     ZRB_REQUIRE(n >= 0 && n <= 16, "at most 16 tensors per call (got %d)", n);
+    if (c->cfg.engine == ZRB_ENGINE_TC) ZRB_TRY(tc_flush_updates(c, (cudaStream_t)stream));
     TensorList tl;
     tl.count = n;
     for (int i = 0; i < n; ++i) {

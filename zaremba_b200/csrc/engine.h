@@ -48,6 +48,7 @@ struct zrb_ctx {
     int64_t emb_cap_rows = 0;
     bool keep_clipped = true;              // zrb_train_step_update writes coef * g back into the gradient buffers
     bool emb_sparse = false;               // touch only the rows of the embedding gradient that can be non-zero
+    bool lazy_update = false;              // zrb_set_lazy_update: upper-layer / fc weight updates run beside the next forward
     bool fused_norm = false;               // single process: matrices' part of the clip norm from the wgrad GEMM epilogues
     int64_t emb_prev_cap = 0;              // capacity of emb_prev_ids (tokens)
     unsigned int* resident_flag = nullptr; // written by the backward recurrence kernel once all its CTAs are resident
@@ -95,6 +96,7 @@ int tc_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
                         float* loss, cudaStream_t s);
 int tc_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int l, cudaStream_t s);
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries);
+int tc_flush_updates(zrb_ctx* c, cudaStream_t s);   // apply deferred weight updates now (zrb_set_lazy_update)
 bool tc_persistent_bwd(const zrb_ctx* c);   // the persistent backward recurrence kernel is in use for this context
 int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
               cudaStream_t s);

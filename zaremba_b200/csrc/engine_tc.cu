@@ -29,6 +29,12 @@ struct zrb_tc_state {
     // ~20 SMs it leaves idle): 0 none, 1 = fc.W, 2 = (w_ih, w_hh) of layer `pending_layer`
     int pending = 0, pending_layer = 0;
     bool defer_wgrad = false;
+    // deferred weight updates (zrb_set_lazy_update): items 1..L-1 = (w_ih, w_hh) of that layer, item L = fc.W; bit i of
+    // upd_pending set = item i still to be applied with the (lr, coef in c->scalars[1]) of the step that deferred it
+    unsigned upd_pending = 0;
+    float upd_lr = 0.f;
+    zrb::TensorList upd_tl{};
+    bool in_train_step = false;   // tc_forward is running as the first half of a fused train step
     float* colsum_scratch = nullptr;   // row-split partials of the bias-gradient column sums
     int64_t packed_version = 0;
     zrb_params packed_params{};
@@ -53,6 +59,7 @@ struct zrb_tc_state {
 
 namespace zrb {
 
+static bool prof_keeps_pdl();
 static int pad64(int n) { return (n + 63) / 64 * 64; }
 
 template <typename T>
@@ -101,10 +108,10 @@ int tc_ctx_init(zrb_ctx* c) {
     if (t->fplan.ok) {
         const RecPlan& fp = t->fplan;
         for (int l = 0; l < L; ++l) {
-            ZRB_TRY(tc_alloc(c, &t->w_img_f[l], (size_t)fp.nCTA * fp.Kc * fp.G * 64));
-            ZRB_TRY(tc_alloc(c, &t->h0_img[l], (size_t)fp.Kc * fp.GB * 64));
+            ZRB_TRY(tc_alloc(c, &t->w_img_f[l], (size_t)fp.nCTA * fp.KcS * fp.G * 64 + 16 * 64 /* M=128 over-read */));
+            ZRB_TRY(tc_alloc(c, &t->h0_img[l], (size_t)fp.Kc * fp.GBi * 64));
         }
-        ZRB_TRY(tc_alloc(c, &t->h_img, (size_t)(c->cfg.max_seq + 1) * fp.Kc * fp.GB * 64));
+        ZRB_TRY(tc_alloc(c, &t->h_img, (size_t)(c->cfg.max_seq + 1) * fp.Kc * fp.GBi * 64));
         ZRB_TRY(tc_alloc(c, &t->counter, 64));
     }
     if (getenv("ZRB_REC_TRACE")) ZRB_TRY(tc_alloc(c, &t->trace, (size_t)2 * c->cfg.max_seq * 8));
@@ -112,8 +119,8 @@ int tc_ctx_init(zrb_ctx* c) {
     if (!t->fplan.ok || (force && !strcmp(force, "fwdonly"))) t->bplan.ok = 0;
     if (t->bplan.ok) {
         const RecPlan& bp = t->bplan;
-        for (int l = 0; l < L; ++l) ZRB_TRY(tc_alloc(c, &t->w_img_b[l], (size_t)bp.nCTA * bp.Kc * bp.G * 64));
-        ZRB_TRY(tc_alloc(c, &t->g_img, (size_t)2 * 4 * bp.Kc * bp.GB * 64));
+        for (int l = 0; l < L; ++l) ZRB_TRY(tc_alloc(c, &t->w_img_b[l], (size_t)bp.nCTA * bp.KcS * bp.G * 64 + 16 * 64));
+        ZRB_TRY(tc_alloc(c, &t->g_img, (size_t)2 * 4 * bp.Kc * bp.GBi * 64));
     }
     return ZRB_OK;
 }
@@ -143,12 +150,45 @@ static int tc_pack_weights(zrb_ctx* c, const zrb_params* p, cudaStream_t s) {
     return ZRB_OK;
 }
 
+// apply deferred update item `item` (see zrb_tc_state::upd_pending); pdl: as a programmatic dependent of the forward
+// recurrence kernel just enqueued on `s`
+static int tc_issue_update(zrb_ctx* c, int item, bool pdl, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
+    if (!(t->upd_pending & (1u << item))) return ZRB_OK;
+    t->upd_pending &= ~(1u << item);
+    const TensorList& tl = t->upd_tl;
+    const bool persistent = t->fplan.ok && t->bplan.ok;
+    if (item < L) {
+        const int l = item, b = 1 + 4 * l;
+        ZRB_TRY(update_pack(tl.p[b], tl.g[b], 4 * H, H, t->upd_lr, c->scalars, t->w_ih_h[l], t->Hp, nullptr, nullptr,
+                            nullptr, nullptr, c->keep_clipped, s, pdl));
+        return update_pack(tl.p[b + 1], tl.g[b + 1], 4 * H, H, t->upd_lr, c->scalars, persistent ? nullptr : t->w_hh_h[l],
+                           t->Hp, t->fplan.ok ? t->w_img_f[l] : nullptr, &t->fplan,
+                           t->bplan.ok ? t->w_img_b[l] : nullptr, &t->bplan, c->keep_clipped, s, pdl);
+    }
+    const int f = 1 + 4 * L;
+    return update_pack(tl.p[f], tl.g[f], V, H, t->upd_lr, c->scalars, t->fc_w_h, t->Hp, nullptr, nullptr, nullptr,
+                       nullptr, c->keep_clipped, s, pdl);
+}
+
+int tc_flush_updates(zrb_ctx* c, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    if (!t || !t->upd_pending) return ZRB_OK;
+    ProfScope ps(c, ZRB_PROF_CLIP_SGD, s);
+    for (int item = 1; item <= c->cfg.layers; ++item) ZRB_TRY(tc_issue_update(c, item, false, s));
+    return ZRB_OK;
+}
+
 int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_states* in, const zrb_states* out,
                float* scores, cudaStream_t s) {
     zrb_tc_state* t = c->tc;
     const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab, T = c->T, B = c->B, N = T * B;
     const int Hp = t->Hp;
     const size_t bh = (size_t)B * H * sizeof(float);
+    // deferred updates ride beside the forward recurrences of a fused train step; any other forward applies them first
+    const bool ride = t->upd_pending && t->in_train_step && t->fplan.ok && (!c->prof_on || prof_keeps_pdl());
+    if (t->upd_pending && !ride) ZRB_TRY(tc_flush_updates(c, s));
     ZRB_TRY(tc_pack_weights(c, p, s));
     {   // state copies (in / out may be the same buffers), fp16 h0 rows and images, saved tokens: one launch
         FwdPrep fp = {};
@@ -157,7 +197,7 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
             fp.hprev_h[l] = t->hprev_h[l]; fp.h0_img[l] = t->fplan.ok ? t->h0_img[l] : nullptr;
         }
         fp.x = x; fp.x_saved = c->x_saved;
-        fp.L = L; fp.B = B; fp.H = H; fp.Hp = Hp; fp.GB = t->fplan.GB; fp.Kc = t->fplan.Kc; fp.N = N;
+        fp.L = L; fp.B = B; fp.H = H; fp.Hp = Hp; fp.GB = t->fplan.GBi; fp.Kc = t->fplan.Kc; fp.N = N;
         ZRB_TRY(fwd_prep(fp, s));
     }
     {
@@ -183,6 +223,9 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
                                  out->c[l], t->hprev_h[l], t->x_h[l + 1], t->counter, t->cnt_f, T, B, H, Hp, m, s,
                                  t->trace));
             t->cnt_f += arrivals;
+            // deferred update of the NEXT layer's matrices (or of fc.W after the last layer): on the idle SMs, beside
+            // this recurrence; their consumers (the next input GEMM / the projection) are enqueued behind them
+            if (ride) ZRB_TRY(tc_issue_update(c, l + 1, true, s));
             continue;
         }
         for (int tt = 0; tt < T; ++tt) {
@@ -382,7 +425,10 @@ int tc_train_step_grads(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
                         float* loss, cudaStream_t s) {
     c->T = T; c->B = B; c->train = 1; c->seed = seed; c->step = step;
     c->have_fwd = false;
-    ZRB_TRY(tc_forward(c, p, x, in, out, c->scores, s));
+    c->tc->in_train_step = true;
+    const int frc = tc_forward(c, p, x, in, out, c->scores, s);
+    c->tc->in_train_step = false;
+    ZRB_TRY(frc);
     c->have_fwd = true;
     {
         ProfScope ps(c, ZRB_PROF_SOFTMAX, s);
@@ -397,7 +443,10 @@ int tc_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
                         float* loss, cudaStream_t s) {
     c->T = T; c->B = B; c->train = 1; c->seed = seed; c->step = step;
     c->have_fwd = false;
-    ZRB_TRY(tc_forward(c, p, x, in, out, c->scores, s));
+    c->tc->in_train_step = true;
+    const int frc = tc_forward(c, p, x, in, out, c->scores, s);
+    c->tc->in_train_step = false;
+    ZRB_TRY(frc);
     c->have_fwd = true;
     {
         ProfScope ps(c, ZRB_PROF_SOFTMAX, s);
@@ -429,6 +478,7 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
               cudaStream_t s) {
     zrb_tc_state* t = c->tc;
     const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
+    ZRB_TRY(tc_flush_updates(c, s));   // (a second update without a forward in between)
     bool fuse = true;   // update_pack picks 16 / 8 / 4-byte accesses from the matrix width and alignment
     for (int i = 0; i < tl.count && fuse; ++i)
         fuse = ((((uintptr_t)tl.p[i]) | ((uintptr_t)tl.g[i])) & 3) == 0;
@@ -463,19 +513,31 @@ int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, f
     auto push = [&](int i) { rest.p[rest.count] = tl.p[i]; rest.g[rest.count] = tl.g[i]; rest.n[rest.count] = tl.n[i]; rest.count++; };
     if (!rows_only) push(0);
     const bool persistent = t->fplan.ok && t->bplan.ok;
+    // lazy update: layer 0 (needed by the very next kernels) now; layers >= 1 and fc.W beside the forward recurrences of
+    // the next step (tc_forward), or at the next call that is not a fused train step (tc_flush_updates)
+    const bool lazy = c->lazy_update && persistent && (!c->prof_on || prof_keeps_pdl());
+    if (lazy) {
+        t->upd_tl = tl;
+        t->upd_lr = lr;
+    }
     for (int l = 0; l < L; ++l) {
         const int b = 1 + 4 * l;
+        push(b + 2);
+        push(b + 3);
+        if (lazy && l >= 1) {
+            t->upd_pending |= 1u << l;
+            continue;
+        }
         ZRB_TRY(update_pack(tl.p[b], tl.g[b], 4 * H, H, lr, c->scalars, t->w_ih_h[l], t->Hp, nullptr, nullptr, nullptr,
                             nullptr, c->keep_clipped, s));
         ZRB_TRY(update_pack(tl.p[b + 1], tl.g[b + 1], 4 * H, H, lr, c->scalars, persistent ? nullptr : t->w_hh_h[l],
                             t->Hp, t->fplan.ok ? t->w_img_f[l] : nullptr, &t->fplan,
                             t->bplan.ok ? t->w_img_b[l] : nullptr, &t->bplan, c->keep_clipped, s));
-        push(b + 2);
-        push(b + 3);
     }
     const int f = 1 + 4 * L;
-    ZRB_TRY(update_pack(tl.p[f], tl.g[f], V, H, lr, c->scalars, t->fc_w_h, t->Hp, nullptr, nullptr, nullptr, nullptr,
-                        c->keep_clipped, s));
+    if (lazy) t->upd_pending |= 1u << L;
+    else ZRB_TRY(update_pack(tl.p[f], tl.g[f], V, H, lr, c->scalars, t->fc_w_h, t->Hp, nullptr, nullptr, nullptr, nullptr,
+                             c->keep_clipped, s));
     push(f + 1);
     ZRB_TRY(sgd_apply(rest, lr, c->scalars, c->keep_clipped, s));
     t->wg_ok = false;

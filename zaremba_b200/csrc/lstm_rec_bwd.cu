@@ -40,6 +40,7 @@ struct RecBwdArgs {
     unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
     unsigned int base;
     int T, B, H, G4p, U, G, GB, Kc, nCTA;
+    int KcS, GBi;             // K chunks per CTA (Kc / S); 8-row batch groups of the dG images (GB, or 4 when N = 32)
     MaskSrc m;
     long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
 };
@@ -86,12 +87,20 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// S = 1: clusters of 4 (CTA rank = gate), M = 64 tiles, the whole gate block as contraction (S = 1 also keeps the
+//        staging + DSMEM-pull exchange selectable with a.push = 0).
+// S = 2: clusters of 8.  The MMA phase costs one instruction per K step whatever the tile height, so the cluster owns
+//        twice the units (8U = 96 rows, M = 128, N = 32) and CTA rank r = 2*gate + half multiplies only HALF of its gate's
+//        rows: 47 instructions per step instead of 94, half the operand image to fetch; the eight partial products are
+//        pushed (st.async) into the owners' shared memory and summed in fixed order.
+template <int S>
 __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs a) {
+    constexpr int CS = 4 * S;   // cluster size
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    const int a_bytes = a.Kc * a.G * 128;
-    const int b_bytes = a.Kc * a.GB * 128;
-    const int Bp = a.GB * 8;
+    const int a_bytes = a.KcS * a.G * 128;     // this CTA's weight slice
+    const int b_bytes = a.KcS * a.GBi * 128;   // the part of its gate's dG image this CTA multiplies with
+    const int Bp = a.GBi * 8;                  // N of the MMA
     const int ldd = Bp + 1;
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;
@@ -110,13 +119,14 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int cluster = blockIdx.x >> 2;
-    const int UC = 4 * a.U;
+    const int cluster = blockIdx.x / CS;
+    const int UC = CS * a.U;
     const int jc0 = cluster * UC;            // first unit of the cluster
     const int j0 = jc0 + (int)rank * a.U;    // first unit whose cell math this CTA owns
     const int nu = max(0, min(a.U, a.H - j0));
+    const int gate = (int)rank / S, khalf = (int)rank % S;   // contraction slice: rows [khalf*KcS*8, +KcS*8) of gate block `gate`
     const int T = a.T, B = a.B, H = a.H;
-    const int ksteps = a.Kc / 2;
+    const int ksteps = a.KcS / 2;
     const int piece_steps = (ksteps + kRecPieces - 1) / kRecPieces;
     const bool tr = a.trace != nullptr && blockIdx.x == 0;
 
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         mbar_init(bar_a, 1);
         for (int i = 0; i < kRecPieces; ++i) mbar_init(&bar_b[i], 1);
         mbar_init(bar_mma, kRecMmaWarps);
-        mbar_init(bar_part, 4);
+        mbar_init(bar_part, CS);
         mbar_init(bar_recv, 1);
         fence_mbar_init();
     }
@@ -138,10 +148,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
 
     if (warp == kRecLoadWarp && lane == 0) {
         // ===================== loader =====================
-        const uint8_t* src = (const uint8_t*)a.w_img + ((size_t)cluster * 4 + rank) * a_bytes;
+        const uint8_t* src = (const uint8_t*)a.w_img + ((size_t)cluster * CS + rank) * a_bytes;
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
-        const int lbo_b = a.GB * 128;
+        const int lbo_b = a.GBi * 128;
+        const size_t gate_bytes = (size_t)a.Kc * a.GBi * 128;   // one gate's whole dG image
         const bool publish = a.res_flag != nullptr && blockIdx.x == 0;
         if (publish && T == 1) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.res_flag), "r"(a.res_value) : "memory");
         for (int s = 1; s < T; ++s) {
@@ -151,7 +162,8 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.res_flag), "r"(a.res_value) : "memory");
             if (tr) a.trace[s * 8 + 0] = clock64();
             fence_proxy_async_global();
-            const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + rank) * b_bytes;
+            const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + gate) * gate_bytes +
+                                 (size_t)khalf * b_bytes;
             for (int pc = 0; pc < kRecPieces; ++pc) {
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
                 if (k0 >= k1) { mbar_arrive(&bar_b[pc]); continue; }
@@ -164,9 +176,9 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         // ===================== MMA issuers: issuer i takes K steps i, i+2, ... into accumulator i =====================
         const int me = warp - kRecMmaWarp;
         const uint32_t my_acc = tmem_d + me * 32;
-        const uint32_t idesc = make_idesc_f16(64, Bp, 0, 0);
+        const uint32_t idesc = make_idesc_f16(S == 2 ? 128 : 64, Bp, 0, 0);
         const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-        const uint32_t lbo_a = a.G * 128, lbo_b = a.GB * 128;
+        const uint32_t lbo_a = a.G * 128, lbo_b = a.GBi * 128;
         bounded_mbar_wait(bar_a, 0);
         for (int s = 1; s < T; ++s) {
             for (int pc = 0; pc < kRecPieces; ++pc) {
@@ -198,12 +210,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         const uint32_t sD_addr = smem_u32(sD);
         uint32_t part_addr[4];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) part_addr[rr] = mapa_shared(sD_addr, rr);
+        for (int rr = 0; rr < 4; ++rr) part_addr[rr] = mapa_shared(sD_addr, rr);   // (pull exchange: S == 1 only)
         const uint32_t bar_part_addr = smem_u32(bar_part);
         const uint32_t sR_addr = smem_u32(sR), bar_recv_addr = smem_u32(bar_recv);
-        const uint32_t recv_bytes = 4u * (uint32_t)a.U * (uint32_t)Bp * 4u;   // 4 sources x U units x Bp columns
+        const uint32_t recv_bytes = (uint32_t)CS * (uint32_t)a.U * (uint32_t)Bp * 4u;   // CS sources x U units x Bp columns
         const float inv = 1.f / kGradScale;
-        const size_t img_gate = (size_t)a.Kc * a.GB * 64;
+        const size_t img_gate = (size_t)a.Kc * a.GBi * 64;
+        const bool push = S == 2 || a.push != 0;
 
         for (int s = 0; s < T; ++s) {
             const int t = T - 1 - s;
@@ -228,7 +241,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 }
             }
             if (s > 0) {
-                if (a.push && tid == 0) mbar_expect_tx(bar_recv, recv_bytes);
+                if (push && tid == 0) mbar_expect_tx(bar_recv, recv_bytes);
                 bounded_mbar_wait(bar_mma, (s - 1) & 1);
                 tcgen05_fence_after();
                 if (tr && tid == 0) a.trace[s * 8 + 3] = clock64();
@@ -236,8 +249,9 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
                     // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
                     // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
-                    for (int task = warp; task < 4 * a.GB; task += kRecEpiWarps) {
+                    for (int task = warp; task < 4 * a.GBi; task += kRecEpiWarps) {
                         const int quad = task & 3, c0 = (task >> 2) * 8;
+                        if (S == 2 && 32 * quad >= UC) continue;          // M = 128: row i sits in lane i; padding quadrant
                         uint32_t v[kRecMmaWarps][8];
                         const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
 #pragma unroll
@@ -253,9 +267,9 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(v[ai][i]);
                             }
-                        if (lane < 16) {
-                            const int row = 16 * quad + lane;               // cluster-local unit of this accumulator row
-                            if (!a.push) {
+                        if (S == 2 || lane < 16) {
+                            const int row = S == 2 ? 32 * quad + lane : 16 * quad + lane;   // cluster-local unit of this row
+                            if (!push) {
                                 float* dst = sD + row * ldd + c0;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) dst[i] = acc[i];
@@ -271,7 +285,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     }
                 }
                 tcgen05_fence_before();
-                if (!a.push) {
+                if (!push) {
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
                     if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     }
                 } else {
                     if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
-                    bounded_mbar_wait(bar_recv, (s - 1) & 1);   // all 4 x U x Bp partial sums of my units have landed
+                    bounded_mbar_wait(bar_recv, (s - 1) & 1);   // all CS x U x Bp partial sums of my units have landed
                 }
             }
             if (tr && tid == 0) a.trace[s * 8 + 5] = clock64();
@@ -300,16 +314,17 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 if (!ok) continue;
                 float dh = dyv[k];
                 if (s > 0) {
-                    float pp[4];
-                    if (!a.push) {
+                    float pp[CS];
+                    if (!push) {
                         const uint32_t off = (uint32_t)(((int)rank * a.U + u) * ldd + b) * 4u;
 #pragma unroll             // issue all four DSMEM loads before the first use (each is ~200+ clk)
                         for (int rr = 0; rr < 4; ++rr) pp[rr] = ld_dsmem_f32(part_addr[rr] + off);
                     } else {
 #pragma unroll
-                        for (int rr = 0; rr < 4; ++rr) pp[rr] = sR[(rr * a.U + u) * ldr + b];
+                        for (int rr = 0; rr < CS; ++rr) pp[rr] = sR[(rr * a.U + u) * ldr + b];
                     }
                     float r = (pp[0] + pp[1]) + (pp[2] + pp[3]);
+                    if constexpr (S == 2) r += (pp[4] + pp[5]) + (pp[6] + pp[7]);
                     dh += r * inv;
                 }
                 const float tc = fast_tanh(ct[k]);
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 dg4[3] = d_o * go[k] * (1.f - go[k]);
                 const int j = j0 + u;
                 // critical path: the four gate images the next step multiplies with
-                __half* img = a.g_img + (size_t)(t & 1) * 4 * img_gate + ((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 +
+                __half* img = a.g_img + (size_t)(t & 1) * 4 * img_gate + ((size_t)(j >> 3) * a.GBi + (b >> 3)) * 64 +
                               (b & 7) * 8 + (j & 7);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -385,39 +400,96 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     cluster_sync_all();   // no CTA leaves while a peer may still read its staged partial
 }
 
-// w_img[cluster][r][kc][g][rr][e] = half(W_hh[r*H + kc*8+e, cluster*UC + g*8+rr]): one warp per (cluster, r, kc)
-// reads 8 rows x UC contiguous floats and writes one contiguous 16*UC-byte block.
-__global__ void pack_whh_bwd_kernel(const float* __restrict__ W, __half* __restrict__ img, int H, int UC, int G, int Kc,
-                                    int nCluster) {
-    __shared__ __half tile[8][8 * 64];
+// w_img[cluster][rank][kcl][g][rr][e] = half(W_hh[gate*H + (khalf*KcS + kcl)*8 + e, cluster*UC + g*8 + rr]) with
+// rank = gate*S + khalf: one warp per (cluster, rank, kcl) reads 8 rows x UC contiguous floats and writes one contiguous
+// 16*UC-byte block.
+__global__ void pack_whh_bwd_kernel(const float* __restrict__ W, __half* __restrict__ img, int H, int UC, int G, int KcS,
+                                    int S, int nCluster) {
+    __shared__ __half tile[8][8 * 128];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long total = (long long)nCluster * 4 * Kc;
+    const int CS = 4 * S;
+    const long long total = (long long)nCluster * CS * KcS;
     for (long long w = (long long)blockIdx.x * 8 + warp_in_block; w < total; w += (long long)gridDim.x * 8) {
-        const int kc = (int)(w % Kc);
-        const int r = (int)((w / Kc) & 3);
-        const int cl = (int)(w / ((long long)Kc * 4));
+        const int kcl = (int)(w % KcS);
+        const int r = (int)((w / KcS) % CS);
+        const int cl = (int)(w / ((long long)KcS * CS));
+        const int gate = r / S, khalf = r % S;
         __half* t = tile[warp_in_block];
         const int rows8 = G * 8;
         for (int idx = lane; idx < 8 * rows8; idx += 32) {
             int e = idx / rows8, u = idx % rows8;            // u fastest: contiguous global reads
-            int k = kc * 8 + e, j = cl * UC + u;
-            float v = (k < H && u < UC && j < H) ? W[((size_t)r * H + k) * H + j] : 0.f;
+            int k = (khalf * KcS + kcl) * 8 + e, j = cl * UC + u;
+            float v = (k < H && u < UC && j < H) ? W[((size_t)gate * H + k) * H + j] : 0.f;
             t[u * 8 + e] = __float2half_rn(v);
         }
         __syncwarp();
-        __half* dst = img + (((size_t)cl * 4 + r) * Kc + kc) * ((size_t)G * 64);
+        __half* dst = img + (((size_t)cl * CS + r) * KcS + kcl) * ((size_t)G * 64);
         for (int idx = lane; idx < rows8 * 8; idx += 32) dst[idx] = t[idx];
         __syncwarp();
     }
 }
 
+static bool rec_bwd_no_coop() {
+    // Profilers (Nsight Compute) refuse cooperative + cluster launches; under one (detected through the injection
+    // environment it sets up) or with ZRB_NO_COOP=1 the kernel is launched as a plain cluster launch after an occupancy
+    // check that the whole grid fits the device.  Without the cooperative guarantee another context holding SMs (MPS, a
+    // concurrent kernel) could leave CTAs unscheduled; the barrier waits are bounded and trap after ~3 s instead of hanging.
+    static const bool v = getenv("ZRB_NO_COOP") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                          getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NVTX_INJECTION64_PATH") != nullptr;
+    return v;
+}
+
+template <int S>
+static int rec_bwd_max_clusters(int smem) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * S * 64);
+    cfg.blockDim = dim3(kRecThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4 * S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaFuncSetAttribute(lstm_rec_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n, lstm_rec_bwd_kernel<S>, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int rec_bwd_plan(int H, int B, RecPlan* plan) {
     int nsm = tc_num_sms();
-    int Kp = (H + 15) / 16 * 16;
-    plan->Kc = Kp / 8;
     plan->GB = (B + 7) / 8;
     plan->ok = 0;
+    plan->KS = 1;
     if (plan->GB * 8 > 32) return ZRB_OK;
+    static const bool no_split = getenv("ZRB_REC_NOSPLIT") != nullptr;   // A/B switch
+    // clusters of 8, half a gate block per CTA (see the kernel header); M = 128 needs N % 16 == 0
+    if (!no_split && H >= 256) {
+        const int Kp = (H + 31) / 32 * 32, Kc = Kp / 8, KcS = Kc / 2, GBi = (plan->GB + 1) / 2 * 2;
+        // first choice: at most one (unit, batch) cell per epilogue thread (see rec_fwd_plan)
+        for (int pass = 0; pass < 2; ++pass)
+            for (int U = 16; U >= 1; --U) {
+                const int UC = 8 * U;
+                if (UC > 128) continue;
+                const int ncl = (H + UC - 1) / UC;
+                if (ncl * 8 > nsm) break;
+                if (U * B > (pass == 0 ? 1 : kRecMaxCell) * kRecEpiThreads) continue;
+                const int G = UC / 8;
+                const size_t smem = rec_smem_bytes(KcS, G, GBi);
+                if (smem <= 227 * 1024 && 8 * U * (GBi * 8 + 4) <= 2 * 64 * (GBi * 8 + 1)) {
+                    if (rec_bwd_max_clusters<2>((int)smem) < ncl) continue;   // the GPCs cannot hold that many 8-CTA clusters
+                    plan->KS = 2; plan->U = U; plan->G = G; plan->nCTA = ncl * 8; plan->smem = (int)smem;
+                    plan->Kc = Kc; plan->KcS = KcS; plan->GBi = GBi; plan->ok = 1;
+                    return ZRB_OK;
+                }
+            }
+    }
+    int Kp = (H + 15) / 16 * 16;
+    plan->Kc = Kp / 8;
+    plan->KcS = plan->Kc;
+    plan->GBi = plan->GB;
     int max_clusters = (nsm - 16) / 4;   // clusters of 4 strand up to 16 SMs (GPC remainders)
     for (int U = 16; U >= 1; --U) {
         int UC = 4 * U;
@@ -435,31 +507,23 @@ int rec_bwd_plan(int H, int B, RecPlan* plan) {
 }
 
 int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s) {
-    pack_whh_bwd_kernel<<<148 * 4, 256, 0, s>>>(W, img, H, 4 * p.U, p.G, p.Kc, p.nCTA / 4);
+    const int CS = 4 * p.KS;
+    pack_whh_bwd_kernel<<<148 * 4, 256, 0, s>>>(W, img, H, CS * p.U, p.G, p.KcS, p.KS, p.nCTA / CS);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
 
-int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
-                 const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
-                 int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace, float* db1, float* db2,
-                 unsigned int* resident_flag, unsigned int resident_value, float* db_scratch) {
-    ZRB_REQUIRE(!db1 || db_scratch, "bias gradients need the scratch buffer");
+template <int S>
+static int launch_rec_bwd(const RecPlan& p, const RecBwdArgs& a, cudaStream_t s) {
+    constexpr int CS = 4 * S;
     static bool attr[64] = {};   // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
     if (!attr[dev]) {
-        ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr[dev] = true;
     }
-    RecBwdArgs a;
-    a.base = counter_base;
-    a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
-    static const bool pull = getenv("ZRB_BWD_PULL") != nullptr;   // A/B switch: the r01 staging + DSMEM-pull exchange
-    a.push = pull ? 0 : 1;
-    a.counter = counter; a.db1 = db1; a.db2 = db2; a.db_scratch = db_scratch; a.res_flag = resident_flag; a.res_value = resident_value;
-    a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.nCTA);
     cfg.blockDim = dim3(kRecThreads);
@@ -467,23 +531,17 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     cfg.stream = s;
     cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     attrs[1].id = cudaLaunchAttributeCooperative;
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
     // The grid barrier needs all nCTA CTAs co-resident.  The cooperative attribute makes the driver guarantee it (or
-    // refuse the launch).  Profilers (Nsight Compute) refuse the cooperative + cluster combination, so under a
-    // profiler -- detected through the injection environment it sets up, or forced with ZRB_NO_COOP=1 -- the kernel is
-    // launched as a plain cluster launch AFTER checking with the occupancy API that the whole grid fits the device
-    // (one CTA per SM, clusters of 4).  Without the guarantee, another context holding SMs (MPS, a concurrent
-    // kernel) could leave CTAs unscheduled; the barrier waits are bounded and trap after ~3 s instead of hanging.
-    static const bool no_coop = getenv("ZRB_NO_COOP") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
-                                getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
-                                getenv("NVTX_INJECTION64_PATH") != nullptr;
-    cfg.numAttrs = no_coop ? 1 : 2;
+    // refuse the launch); see rec_bwd_no_coop() for the profiler case.
+    const bool no_coop = rec_bwd_no_coop();
     cudaError_t e = cudaSuccess;
     if (!no_coop) {
-        e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel<S>, a);
         if (e == cudaErrorCooperativeLaunchTooLarge) {
             (void)cudaGetLastError();
             set_error("lstm_rec_bwd: the %d-CTA grid cannot be co-resident on this device (cooperative launch too large)",
@@ -495,14 +553,14 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     if (no_coop || e != cudaSuccess) {
         cfg.numAttrs = 1;
         int max_clusters = 0;
-        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_bwd_kernel, &cfg);
-        if (oe != cudaSuccess || max_clusters * 4 < p.nCTA) {
+        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_bwd_kernel<S>, &cfg);
+        if (oe != cudaSuccess || max_clusters * CS < p.nCTA) {
             (void)cudaGetLastError();
-            set_error("lstm_rec_bwd: %d clusters of 4 needed, the device can hold %d at once (%s)", p.nCTA / 4,
+            set_error("lstm_rec_bwd: %d clusters of %d needed, the device can hold %d at once (%s)", p.nCTA / CS, CS,
                       max_clusters, oe == cudaSuccess ? "grid would not be co-resident" : cudaGetErrorString(oe));
             return ZRB_E_CUDA;
         }
-        e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel, a);
+        e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel<S>, a);
     }
     if (e != cudaSuccess) {
         set_error("lstm_rec_bwd launch failed: %s", cudaGetErrorString(e));
@@ -510,6 +568,22 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     }
     count_launch();
     return ZRB_OK;
+}
+
+int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
+                 const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
+                 int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace, float* db1, float* db2,
+                 unsigned int* resident_flag, unsigned int resident_value, float* db_scratch) {
+    ZRB_REQUIRE(!db1 || db_scratch, "bias gradients need the scratch buffer");
+    RecBwdArgs a;
+    a.base = counter_base;
+    a.w_img = w_img; a.g_img = g_img; a.dy = dy; a.gates = gates; a.cst = cst; a.c0 = c0; a.dG_h = dG_h;
+    static const bool pull = getenv("ZRB_BWD_PULL") != nullptr;   // A/B switch: the r01 staging + DSMEM-pull exchange (S = 1)
+    a.push = pull ? 0 : 1;
+    a.counter = counter; a.db1 = db1; a.db2 = db2; a.db_scratch = db_scratch; a.res_flag = resident_flag; a.res_value = resident_value;
+    a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
+    a.KcS = p.KcS; a.GBi = p.GBi;
+    return p.KS == 2 ? launch_rec_bwd<2>(p, a, s) : launch_rec_bwd<1>(p, a, s);
 }
 
 }  // namespace zrb

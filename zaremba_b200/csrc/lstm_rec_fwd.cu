@@ -29,12 +29,21 @@
 // Roofline: latency/L2/shared-memory bound, not tensor bound -- per step each CTA streams its 144 KB
 // weight slice from shared memory through the tensor core (>= 1150 clk at 128 B/clk) and all CTAs
 // re-read the 72 KB h image from L2; algorithmic flops per layer call = 8*T*B*H^2.
+#include <stdlib.h>
+
 #include "rec_common.cuh"
 
 namespace zrb {
 
+// K-split variant (RecPlan::KS == 2, used when the shape allows): the MMA phase is 1 instruction per K step of 16
+// whatever the tile height (M = 64 and M = 128 cost the same ~33 clk at N <= 48), so a CTA that owns 4U = 48 gate rows and
+// the whole contraction issues H/16 = 94 half-empty M=64 instructions per step.  A CLUSTER OF TWO CTAs instead owns 2U
+// units = 96 gate rows (M = 128, N = 32): CTA r keeps the K half r of all 96 rows resident (same 144 KB), loads only
+// its half of the h image, issues 47 instructions, and pushes each accumulator row straight from registers into the
+// shared memory of the CTA that owns the row's unit (st.async, bytes counted on the owner's mbarrier: no fence, no
+// staging pass); the owner adds the two partial sums in its cell math.
 struct RecFwdArgs {
-    const __half* w_img;      // [nCTA][Kc][G][8][8]
+    const __half* w_img;      // [nCTA][KcS][G][8][8]  (K-split: CTA = (pair, K half))
     const __half* h0_img;     // [Kc][GB][8][8] image of the state entering the window: the B operand of step 0
     __half* h_img;            // [T+1][Kc][GB][8][8]; image t (t >= 1) is the B operand of step t, written by step t-1
     float* gates;             // [N,4H] in: x-part pre-activations (+biases); out: activated gates
@@ -47,32 +56,56 @@ struct RecFwdArgs {
     unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
     unsigned int base;
     int T, B, H, Hp, U, G, GB, Kc, nCTA;
+    int KcS, GBi;             // K chunks per CTA (Kc / KS); 8-row batch groups of the operand image (GB, or 4 when N = 32)
     MaskSrc m;
     long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
 };
 
+__device__ __forceinline__ uint32_t fwd_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t fwd_mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void fwd_st_async_v4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void fwd_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    const int a_bytes = a.Kc * a.G * 128;
-    const int b_bytes = a.Kc * a.GB * 128;
-    const int Bp = a.GB * 8;
+    const int a_bytes = a.KcS * a.G * 128;     // this CTA's weight slice
+    const int b_bytes = a.KcS * a.GBi * 128;   // the part of the h image this CTA multiplies with
+    const int Bp = a.GBi * 8;                  // N of the MMA
     const int ldd = Bp + 1;
+    const int ldr = Bp + 4;                    // K-split: pitch of the receive buffer rows (16-byte aligned)
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;
-    float* sD = (float*)(sB + b_bytes);                       // [64][Bp+1] accumulator staging (sized for two)
+    float* sD = (float*)(sB + b_bytes);        // [64][Bp+1] accumulator staging (sized for two) / K-split: receive buffer
+    float* sR = sD;                            //   sR[source rank][gate * U + unit][batch]
     uint64_t* bars = (uint64_t*)((uint8_t*)sD + 2 * 64 * ldd * 4);
     uint64_t* bar_a = bars;        // weight slice landed
     uint64_t* bar_b = bars + 1;    // [kRecPieces] h image pieces of this step landed
     uint64_t* bar_mma = bars + 1 + kRecPieces;  // accumulators ready
-    uint32_t* tmem_slot = (uint32_t*)(bar_mma + 1);
+    uint64_t* bar_recv = bar_mma + 1;           // K-split: both CTAs' partial sums of my rows have landed
+    uint32_t* tmem_slot = (uint32_t*)(bar_recv + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int cta = blockIdx.x;
-    const int j0 = cta * a.U;
-    const int nu = min(a.U, a.H - j0);
-    const int ksteps = a.Kc / 2;
+    const uint32_t rank = SPLIT ? fwd_cluster_ctarank() : 0u;   // K half this CTA multiplies; also which units it owns
+    const int j0 = cta * a.U;                  // (K-split: cta = 2 * pair + rank, the pair owns units [pair*2U, pair*2U + 2U))
+    const int nu = max(0, min(a.U, a.H - j0));
+    const int ksteps = a.KcS / 2;
     const int piece_steps = (ksteps + kRecPieces - 1) / kRecPieces;
     const bool tr = a.trace != nullptr && cta == 0;
 
@@ -80,6 +113,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         mbar_init(bar_a, 1);
         for (int i = 0; i < kRecPieces; ++i) mbar_init(&bar_b[i], 1);
         mbar_init(bar_mma, kRecMmaWarps);
+        mbar_init(bar_recv, 1);
         fence_mbar_init();
     }
     if (warp == kRecMmaWarp) tmem_alloc<kRecTmemCols>(tmem_slot);
@@ -87,6 +121,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    if (SPLIT) fwd_cluster_sync();   // the partner's mbarriers are initialised before any st.async targets them
     if (threadIdx.x == 0) pdl_launch_dependents();
 
     if (warp == kRecLoadWarp && lane == 0) {
@@ -94,12 +129,14 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         const uint8_t* src = (const uint8_t*)a.w_img + (size_t)cta * a_bytes;
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
-        const int lbo_b = a.GB * 128;
+        const int lbo_b = a.GBi * 128;
+        const size_t img_bytes = (size_t)a.Kc * a.GBi * 128;   // one whole h image; this CTA reads K chunks [rank*KcS, +KcS)
         for (int t = 0; t < a.T; ++t) {
             if (t > 0) grid_counter_wait(a.counter, a.base + (unsigned int)t * a.nCTA);
             if (tr) a.trace[t * 8 + 0] = clock64();
             fence_proxy_async_global();
-            const uint8_t* img = t == 0 ? (const uint8_t*)a.h0_img : (const uint8_t*)a.h_img + (size_t)t * b_bytes;
+            const uint8_t* img = (t == 0 ? (const uint8_t*)a.h0_img : (const uint8_t*)a.h_img + (size_t)t * img_bytes) +
+                                 (size_t)rank * b_bytes;
             for (int pc = 0; pc < kRecPieces; ++pc) {
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
                 if (k0 >= k1) { mbar_arrive(&bar_b[pc]); continue; }
@@ -112,9 +149,9 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         // ===================== MMA issuers: issuer i takes K steps i, i+2, ... into accumulator i =====================
         const int me = warp - kRecMmaWarp;
         const uint32_t my_acc = tmem_d + me * 32;
-        const uint32_t idesc = make_idesc_f16(64, Bp, 0, 0);
+        const uint32_t idesc = make_idesc_f16(SPLIT ? 128 : 64, Bp, 0, 0);
         const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-        const uint32_t lbo_a = a.G * 128, lbo_b = a.GB * 128;
+        const uint32_t lbo_a = a.G * 128, lbo_b = a.GBi * 128;
         bounded_mbar_wait(bar_a, 0);
         for (int t = 0; t < a.T; ++t) {
             for (int pc = 0; pc < kRecPieces; ++pc) {
@@ -144,7 +181,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             int b = cell / a.U, u = cell % a.U;
             creg[k] = (cell < cells && u < nu) ? a.c0[(size_t)b * H + j0 + u] : 0.f;
         }
+        const uint32_t sR_addr = smem_u32(sR), bar_recv_addr = smem_u32(bar_recv);
+        const int rows_pair = 8 * a.U;                                   // K-split: gate rows of the pair (4 x 2U)
+        const uint32_t recv_bytes = 2u * 4u * (uint32_t)a.U * (uint32_t)Bp * 4u;   // 2 sources x 4U rows x Bp columns
         for (int t = 0; t < a.T; ++t) {
+            if (SPLIT && tid == 0) mbar_expect_tx(bar_recv, recv_bytes);
             // prefetch the x-part pre-activations of this step while the MMAs run
             float pre[kRecMaxCell][4];
 #pragma unroll
@@ -162,8 +203,9 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
                 // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
                 // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
-                for (int task = warp; task < 4 * a.GB; task += kRecEpiWarps) {
+                for (int task = warp; task < 4 * a.GBi; task += kRecEpiWarps) {
                     const int quad = task & 3, c0 = (task >> 2) * 8;
+                    if (SPLIT && 32 * quad >= rows_pair) continue;        // M = 128: row i sits in lane i; padding quadrant
                     uint32_t v[kRecMmaWarps][8];
                     const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
 #pragma unroll
@@ -179,16 +221,35 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
 #pragma unroll
                             for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(v[ai][i]);
                         }
-                    if (lane < 16) {
-                        float* dst = sD + (16 * quad + lane) * ldd + c0;
+                    if (!SPLIT) {
+                        if (lane < 16) {
+                            float* dst = sD + (16 * quad + lane) * ldd + c0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = acc[i];
+                            for (int i = 0; i < 8; ++i) dst[i] = acc[i];
+                        }
+                    } else {
+                        // row = 4 * (unit within the pair) + gate: straight into the shared memory of the owning CTA
+                        const int row = 32 * quad + lane;
+                        if (row < rows_pair) {
+                            // receive rows are gate-major (q * U + u): the cell threads of a warp (consecutive u) then read
+                            // addresses ldr floats apart, 4 banks apart, instead of 4 * ldr (2 distinct banks: 16-way conflicts)
+                            const int up = row >> 2, owner = up / a.U, lrow = (row & 3) * a.U + (up - owner * a.U);
+                            const uint32_t dst = fwd_mapa(sR_addr + (uint32_t)((((int)rank * 4 * a.U + lrow) * ldr + c0) * 4), owner);
+                            const uint32_t rbar = fwd_mapa(bar_recv_addr, owner);
+                            fwd_st_async_v4(dst, acc[0], acc[1], acc[2], acc[3], rbar);
+                            fwd_st_async_v4(dst + 16, acc[4], acc[5], acc[6], acc[7], rbar);
+                        }
                     }
                 }
             }
             tcgen05_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tr && tid == 0) a.trace[t * 8 + 4] = clock64();
+            if (!SPLIT) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tr && tid == 0) a.trace[t * 8 + 4] = clock64();
+            } else {
+                if (tr && tid == 0) a.trace[t * 8 + 4] = clock64();
+                bounded_mbar_wait(bar_recv, t & 1);   // both K halves of my 4U rows have landed
+            }
             float o_i[kRecMaxCell], o_f[kRecMaxCell], o_g[kRecMaxCell], o_o[kRecMaxCell], o_h[kRecMaxCell];
 #pragma unroll
             for (int k = 0; k < kRecMaxCell; ++k) {
@@ -197,11 +258,22 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 bool ok = cell < cells && u < nu;
                 o_i[k] = o_f[k] = o_g[k] = o_o[k] = o_h[k] = 0.f;
                 if (!ok) continue;
-                const float* d0 = sD + (4 * u) * ldd + b;
-                float zi = pre[k][0] + d0[0];
-                float zf = pre[k][1] + d0[ldd];
-                float zg = pre[k][2] + d0[2 * ldd];
-                float zo = pre[k][3] + d0[3 * ldd];
+                float zi, zf, zg, zo;
+                if (!SPLIT) {
+                    const float* d0 = sD + (4 * u) * ldd + b;
+                    zi = pre[k][0] + d0[0];
+                    zf = pre[k][1] + d0[ldd];
+                    zg = pre[k][2] + d0[2 * ldd];
+                    zo = pre[k][3] + d0[3 * ldd];
+                } else {
+                    const float* r0 = sR + u * ldr + b;                  // K half 0, gate 0
+                    const float* r1 = r0 + 4 * a.U * ldr;                // K half 1
+                    const int gs = a.U * ldr;                            // gate stride
+                    zi = pre[k][0] + (r0[0] + r1[0]);
+                    zf = pre[k][1] + (r0[gs] + r1[gs]);
+                    zg = pre[k][2] + (r0[2 * gs] + r1[2 * gs]);
+                    zo = pre[k][3] + (r0[3 * gs] + r1[3 * gs]);
+                }
                 float gi = fast_sigmoid(zi), gf = fast_sigmoid(zf), gg = fast_tanh(zg), go = fast_sigmoid(zo);
                 float c = gf * creg[k] + gi * gg;
                 float h = go * fast_tanh(c);
@@ -209,8 +281,8 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 o_i[k] = gi; o_f[k] = gf; o_g[k] = gg; o_o[k] = go; o_h[k] = h;
                 // critical path: the next step's operand image [kc][g][r][e], kc = j/8, e = j%8, g = b/8, r = b%8
                 const int j = j0 + u;
-                __half* img = a.h_img + (size_t)(t + 1) * ((size_t)a.Kc * a.GB * 64);
-                img[((size_t)(j >> 3) * a.GB + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7)] = __float2half_rn(h);
+                __half* img = a.h_img + (size_t)(t + 1) * ((size_t)a.Kc * a.GBi * 64);
+                img[((size_t)(j >> 3) * a.GBi + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7)] = __float2half_rn(h);
             }
             if (tr && tid == 0) a.trace[t * 8 + 5] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -245,24 +317,27 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     __syncthreads();
     tcgen05_fence_after();
     if (warp == kRecMmaWarp) tmem_dealloc<kRecTmemCols>(tmem_d);
+    if (SPLIT) fwd_cluster_sync();   // nobody leaves while the partner could still address its shared memory
 }
 
 // ---- weight / state image builders ---------------------------------------------------------------
-// w_img[cta][kc][g][r][e] = half(W_hh[q*H + cta*U + u, kc*8 + e]) with row i = g*8 + r = 4*u + q
-__global__ void pack_whh_fwd_kernel(const float* __restrict__ W, __half* __restrict__ img, int H, int U, int G, int Kc,
-                                    int nCTA) {
-    const size_t per_cta = (size_t)Kc * G * 64;
+// w_img[cta][kcl][g][r][e] = half(W_hh[q*H + j, k]) with cta = cluster * KS + rank, row i = g*8 + r = 4*uc + q,
+// uc = unit within the cluster (UC = KS * U units), j = cluster*UC + uc, k = (rank*KcS + kcl)*8 + e
+__global__ void pack_whh_fwd_kernel(const float* __restrict__ W, __half* __restrict__ img, int H, int UC, int G, int KcS,
+                                    int KS, int nCTA) {
+    const size_t per_cta = (size_t)KcS * G * 64;
     const size_t total = per_cta * nCTA;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         int cta = (int)(idx / per_cta);
         size_t r0 = idx % per_cta;
         int e = (int)(r0 & 7), r = (int)((r0 >> 3) & 7);
-        int g = (int)((r0 >> 6) % G), kc = (int)((r0 >> 6) / G);
-        int i = g * 8 + r, u = i >> 2, q = i & 3;
-        int j = cta * U + u, k = kc * 8 + e;
+        int g = (int)((r0 >> 6) % G), kcl = (int)((r0 >> 6) / G);
+        int i = g * 8 + r, uc = i >> 2, q = i & 3;
+        int cluster = cta / KS, rank = cta % KS;
+        int j = cluster * UC + uc, k = (rank * KcS + kcl) * 8 + e;
         float v = 0.f;
-        if (u < U && j < H && k < H) v = W[((size_t)q * H + j) * H + k];
+        if (uc < UC && j < H && k < H) v = W[((size_t)q * H + j) * H + k];
         img[idx] = __float2half_rn(v);
     }
 }
@@ -272,13 +347,46 @@ size_t rec_smem_bytes(int Kc, int G, int GB) {
     return (size_t)Kc * G * 128 + (size_t)Kc * GB * 128 + 2 * 64 * (GB * 8 + 1) * 4 + 128 /*align*/ + 128 /*bars*/;
 }
 
+static bool rec_no_coop() {
+    // Profilers (Nsight Compute) refuse cooperative + cluster launches; under one (detected through the injection
+    // environment it sets up) or with ZRB_NO_COOP=1 cluster kernels are launched without the cooperative attribute,
+    // after an occupancy check that the whole grid fits the device
+    static const bool v = getenv("ZRB_NO_COOP") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                          getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NVTX_INJECTION64_PATH") != nullptr;
+    return v;
+}
+
 int rec_fwd_plan(int H, int B, RecPlan* plan) {
     int nsm = tc_num_sms();
-    int Kp = (H + 15) / 16 * 16;
-    plan->Kc = Kp / 8;
     plan->GB = (B + 7) / 8;
     plan->ok = 0;
+    plan->KS = 1;
     if (plan->GB * 8 > 32) return ZRB_OK;  // TMEM accumulators / staging sized for N <= 32
+    static const bool no_split = getenv("ZRB_REC_NOSPLIT") != nullptr;   // A/B switch
+    // K-split pairs (see the kernel header): M = 128 needs N % 16 == 0 -> image batch groups padded to an even count
+    if (!no_split && H >= 256) {
+        const int Kp = (H + 31) / 32 * 32, Kc = Kp / 8, KcS = Kc / 2, GBi = (plan->GB + 1) / 2 * 2;
+        // first choice: at most one (unit, batch) cell per epilogue thread -- a second pass of the cell loop for a handful
+        // of cells doubles the critical path of that warp (measured: U = 13, 260 cells, was slower than U = 12)
+        for (int pass = 0; pass < 2; ++pass)
+            for (int U = 16; U >= 1; --U) {
+                const int npair = (H + 2 * U - 1) / (2 * U);
+                if (2 * npair > nsm) break;
+                if (U * B > (pass == 0 ? 1 : kRecMaxCell) * kRecEpiThreads) continue;
+                const int G = U;                              // 8U gate rows of the pair / 8
+                const size_t smem = rec_smem_bytes(KcS, G, GBi);
+                // M = 128 reads 16 row groups per K chunk: the last chunk reaches (16-G)*128 B past the slice, into the h buffer
+                if (smem <= 227 * 1024 && 2 * 4 * U * (GBi * 8 + 4) <= 2 * 64 * (GBi * 8 + 1)) {
+                    plan->KS = 2; plan->U = U; plan->G = G; plan->nCTA = 2 * npair; plan->smem = (int)smem;
+                    plan->Kc = Kc; plan->KcS = KcS; plan->GBi = GBi; plan->ok = 1;
+                    return ZRB_OK;
+                }
+            }
+    }
+    int Kp = (H + 15) / 16 * 16;
+    plan->Kc = Kp / 8;
+    plan->KcS = plan->Kc;
+    plan->GBi = plan->GB;
     for (int U = 16; U >= 1; --U) {
         int n = (H + U - 1) / U;
         if (n > nsm) break;
@@ -295,7 +403,7 @@ int rec_fwd_plan(int H, int B, RecPlan* plan) {
 }
 
 int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s) {
-    pack_whh_fwd_kernel<<<148 * 4, 256, 0, s>>>(W, img, H, p.U, p.G, p.Kc, p.nCTA);
+    pack_whh_fwd_kernel<<<148 * 4, 256, 0, s>>>(W, img, H, p.KS * p.U, p.G, p.KcS, p.KS, p.nCTA);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
@@ -309,17 +417,60 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
     cudaGetDevice(&dev);
     dev &= 63;
     if (!attr[dev]) {
-        ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZRB_CUDA(cudaFuncSetAttribute(lstm_rec_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr[dev] = true;
     }
     RecFwdArgs a;
     a.w_img = w_img; a.h0_img = h0_img; a.h_img = h_img; a.base = counter_base; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;
     a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter;
     a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
+    a.KcS = p.KcS; a.GBi = p.GBi;
     a.trace = trace;
-    void* args[] = {&a};
-    ZRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_kernel, dim3(p.nCTA), dim3(kRecThreads), args,
-                                         (size_t)p.smem, s));
+    if (p.KS == 1) {
+        void* args[] = {&a};
+        ZRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_kernel<false>, dim3(p.nCTA), dim3(kRecThreads), args,
+                                             (size_t)p.smem, s));
+        count_launch();
+        return ZRB_OK;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.nCTA);
+    cfg.blockDim = dim3(kRecThreads);
+    cfg.dynamicSmemBytes = (size_t)p.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cudaError_t e = cudaSuccess;
+    if (!rec_no_coop()) {
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelEx(&cfg, lstm_rec_fwd_kernel<true>, a);
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+            (void)cudaGetLastError();
+            set_error("lstm_rec_fwd: the %d-CTA grid cannot be co-resident on this device", p.nCTA);
+            return ZRB_E_CUDA;
+        }
+        if (e != cudaSuccess) (void)cudaGetLastError();
+    }
+    if (rec_no_coop() || e != cudaSuccess) {
+        cfg.numAttrs = 1;
+        int max_clusters = 0;
+        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_fwd_kernel<true>, &cfg);
+        if (oe != cudaSuccess || max_clusters * 2 < p.nCTA) {
+            (void)cudaGetLastError();
+            set_error("lstm_rec_fwd: %d CTA pairs needed, the device can hold %d at once", p.nCTA / 2, max_clusters);
+            return ZRB_E_CUDA;
+        }
+        e = cudaLaunchKernelEx(&cfg, lstm_rec_fwd_kernel<true>, a);
+    }
+    if (e != cudaSuccess) {
+        set_error("lstm_rec_fwd launch failed: %s", cudaGetErrorString(e));
+        return ZRB_E_CUDA;
+    }
     count_launch();
     return ZRB_OK;
 }

@@ -9,11 +9,21 @@ struct PackSpec {
     __half* row_img;     // [rows, ld] row-major image or null
     int64_t ld;
     __half* fwd_img;     // recurrent forward slices  [cta][kc][g][8][8] or null
-    int fU, fG, fKc;
+    int fU, fG, fKc, fKS;   // units per cluster (KS * U), row groups, K chunks per CTA, K-split factor
     __half* bwd_img;     // recurrent backward slices [cluster][4][kc][g][8][8] or null
-    int bUC, bG, bKc;
+    int bUC, bG, bKc, bS;   // units per cluster, row groups, K chunks per CTA, K-split factor per gate
     int write_g;         // store coef * g back into the gradient buffer (clip_grad_norm_'s in-place scaling)
+    int pdl;             // launched as a programmatic dependent of the forward recurrence kernel enqueued before it
+                         // (deferred update, zrb_set_lazy_update): release the next dependent at once, and block 0 waits
+                         // for the primary before it exits so that the grid cannot complete before the primary has
 };
+
+__device__ __forceinline__ void pdl_prologue(const PackSpec& sp) {
+    if (sp.pdl && threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_epilogue(const PackSpec& sp) {
+    if (sp.pdl && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
@@ -51,6 +61,7 @@ __device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
 template <int VEC>
 __global__ void update_pack_kernel(float* __restrict__ p, float* __restrict__ g, int rows, int cols, float lr,
                                    const float* __restrict__ scalars, PackSpec sp) {
+    pdl_prologue(sp);
     const float coef = scalars[1];
     const int cv = cols / VEC;
     const int64_t total = (int64_t)rows * cv;
@@ -71,6 +82,7 @@ __global__ void update_pack_kernel(float* __restrict__ p, float* __restrict__ g,
             store_halves<VEC>(sp.row_img + (int64_t)r * sp.ld + c, hh);
         }
     }
+    pdl_epilogue(sp);
 }
 
 // W_hh [4H, H] with both recurrent images: a thread owns an 8-row x VEC-column tile (rows j..j+7 of one gate
@@ -79,6 +91,7 @@ __global__ void update_pack_kernel(float* __restrict__ p, float* __restrict__ g,
 template <int VEC>
 __global__ void update_pack_whh_kernel(float* __restrict__ p, float* __restrict__ g, int H, float lr,
                                        const float* __restrict__ scalars, PackSpec sp) {
+    pdl_prologue(sp);
     const float coef = scalars[1];
     const int cv = H / VEC, jb_n = (H + 7) >> 3;
     const int64_t total = (int64_t)4 * jb_n * cv;
@@ -101,8 +114,9 @@ __global__ void update_pack_whh_kernel(float* __restrict__ p, float* __restrict_
                 store_vec<VEC>(p + off, pv);
                 if (sp.row_img) store_halves<VEC>(sp.row_img + ((int64_t)q * H + j) * sp.ld + c, hv[e]);
                 if (sp.fwd_img) {   // slice of the CTA owning unit j, row 4u+q; K indices c..c+VEC-1 share a K chunk
-                    const int cta = j / sp.fU, u = j % sp.fU, row = 4 * u + q;
-                    store_halves<VEC>(sp.fwd_img + (((int64_t)cta * sp.fKc + (c >> 3)) * sp.fG + (row >> 3)) * 64 +
+                    const int cluster = j / sp.fU, u = j % sp.fU, row = 4 * u + q;
+                    const int kc = c >> 3, cta = cluster * sp.fKS + kc / sp.fKc, kcl = kc % sp.fKc;
+                    store_halves<VEC>(sp.fwd_img + (((int64_t)cta * sp.fKc + kcl) * sp.fG + (row >> 3)) * 64 +
                                           (row & 7) * 8 + (c & 7), hv[e]);
                 }
             } else {
@@ -119,38 +133,53 @@ __global__ void update_pack_whh_kernel(float* __restrict__ p, float* __restrict_
                 v.y = (uint32_t)__half_as_ushort(hv[2][x]) | ((uint32_t)__half_as_ushort(hv[3][x]) << 16);
                 v.z = (uint32_t)__half_as_ushort(hv[4][x]) | ((uint32_t)__half_as_ushort(hv[5][x]) << 16);
                 v.w = (uint32_t)__half_as_ushort(hv[6][x]) | ((uint32_t)__half_as_ushort(hv[7][x]) << 16);
-                *reinterpret_cast<uint4*>(sp.bwd_img + ((((int64_t)cl * 4 + q) * sp.bKc + jb) * sp.bG) * 64 + (u >> 3) * 64 +
-                                          (u & 7) * 8) = v;
+                const int rank = q * sp.bS + jb / sp.bKc, kcl = jb % sp.bKc;
+                *reinterpret_cast<uint4*>(sp.bwd_img + ((((int64_t)cl * 4 * sp.bS + rank) * sp.bKc + kcl) * sp.bG) * 64 +
+                                          (u >> 3) * 64 + (u & 7) * 8) = v;
             }
         }
     }
+    pdl_epilogue(sp);
 }
 
 template <int VEC>
 static int update_pack_launch(float* p, float* g, int rows, int cols, float lr, const float* scalars, const PackSpec& sp,
                               bool whh, cudaStream_t s) {
-    if (whh) {
-        int64_t total = (int64_t)4 * ((cols + 7) / 8) * (cols / VEC);
-        int blocks = (int)((total + 127) / 128);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        update_pack_whh_kernel<VEC><<<blocks, 128, 0, s>>>(p, g, cols, lr, scalars, sp);
-    } else {
-        int64_t total = (int64_t)rows * (cols / VEC);
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        update_pack_kernel<VEC><<<blocks, 256, 0, s>>>(p, g, rows, cols, lr, scalars, sp);
+    int64_t total = whh ? (int64_t)4 * ((cols + 7) / 8) * (cols / VEC) : (int64_t)rows * (cols / VEC);
+    const int threads = whh ? 128 : 256;
+    int blocks = (int)((total + threads - 1) / threads);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (sp.pdl) {
+        // beside the persistent forward recurrence: a dynamic shared-memory request larger than what that kernel leaves
+        // free on its SMs keeps these blocks on the ~23 idle SMs, off the latency-critical ones
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 12 * 1024; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (whh) ZRB_CUDA(cudaLaunchKernelEx(&cfg, update_pack_whh_kernel<VEC>, p, g, cols, lr, scalars, sp));
+        else ZRB_CUDA(cudaLaunchKernelEx(&cfg, update_pack_kernel<VEC>, p, g, rows, cols, lr, scalars, sp));
+        count_launch();
+        return ZRB_OK;
     }
+    if (whh) update_pack_whh_kernel<VEC><<<blocks, threads, 0, s>>>(p, g, cols, lr, scalars, sp);
+    else update_pack_kernel<VEC><<<blocks, threads, 0, s>>>(p, g, rows, cols, lr, scalars, sp);
     ZRB_KERNEL_CHECK();
     return ZRB_OK;
 }
 
 int update_pack(float* p, float* g, int rows, int cols, float lr, const float* scalars, __half* row_img, int64_t ld,
-                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, bool write_g, cudaStream_t s) {
+                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, bool write_g, cudaStream_t s,
+                bool pdl) {
     PackSpec sp;
     sp.write_g = write_g ? 1 : 0;
+    sp.pdl = pdl ? 1 : 0;
     sp.row_img = row_img; sp.ld = ld;
-    sp.fwd_img = fwd_img; sp.fU = fp ? fp->U : 1; sp.fG = fp ? fp->G : 1; sp.fKc = fp ? fp->Kc : 1;
-    sp.bwd_img = bwd_img; sp.bUC = bp ? 4 * bp->U : 4; sp.bG = bp ? bp->G : 1; sp.bKc = bp ? bp->Kc : 1;
+    sp.fwd_img = fwd_img; sp.fKS = fp ? fp->KS : 1; sp.fU = fp ? fp->KS * fp->U : 1; sp.fG = fp ? fp->G : 1;
+    sp.fKc = fp ? fp->KcS : 1;
+    sp.bwd_img = bwd_img; sp.bS = bp ? bp->KS : 1; sp.bUC = bp ? 4 * bp->KS * bp->U : 4; sp.bG = bp ? bp->G : 1;
+    sp.bKc = bp ? bp->KcS : 1;
     const bool whh = (fwd_img || bwd_img) && rows == 4 * cols;
     const bool al16 = ((((uintptr_t)p) | ((uintptr_t)g)) & 15) == 0, al8 = ((((uintptr_t)p) | ((uintptr_t)g)) & 7) == 0;
     if (cols % 4 == 0 && al16) return update_pack_launch<4>(p, g, rows, cols, lr, scalars, sp, whh, s);

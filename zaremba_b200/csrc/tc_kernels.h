@@ -26,9 +26,12 @@ struct RecPlan {
     int U;       // hidden units per CTA
     int G;       // 8-row groups of the weight slice (ceil(4U/8))
     int GB;      // 8-row groups of the batch operand (ceil(B/8))
-    int Kc;      // 8-element K chunks (ceil16(H)/8)
+    int Kc;      // 8-element K chunks of the whole contraction
     int nCTA;
     int smem;
+    int KS;      // K-split: CTAs that share one set of output rows, each holding 1/KS of the contraction (clusters)
+    int KcS;     // K chunks per CTA (Kc / KS)
+    int GBi;     // 8-row batch groups of the operand images (GB, or padded so that the MMA's N is a multiple of 16)
 };
 size_t rec_smem_bytes(int Kc, int G, int GB);
 int rec_fwd_plan(int H, int B, RecPlan* plan);
@@ -58,7 +61,8 @@ struct FwdPrep {
 int fwd_prep(const FwdPrep& a, cudaStream_t s);
 // SGD update of one matrix fused with its fp16 image rebuild (optim_tc.cu)
 int update_pack(float* p, float* g, int rows, int cols, float lr, const float* scalars, __half* row_img, int64_t ld,
-                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, bool write_g, cudaStream_t s);
+                __half* fwd_img, const RecPlan* fp, __half* bwd_img, const RecPlan* bp, bool write_g, cudaStream_t s,
+                bool pdl = false);   // pdl: programmatic dependent of the (forward recurrence) kernel enqueued before it
 int rec_bwd_plan(int H, int B, RecPlan* plan);   // U = units per CTA, nCTA = 4 * clusters
 int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s);
 int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,

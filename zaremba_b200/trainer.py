@@ -64,8 +64,14 @@ class _SideStream:
 
 class Trainer:
     def __init__(self, model: Model, batch_size: int, seq_length: int, process_group=None,
-                 keep_clipped_grads: bool = False, data_parallel: bool = True):
-        """data_parallel: when torch.distributed is initialised, shard the batch over the ranks and all-reduce the
+                 keep_clipped_grads: bool = False, data_parallel: bool = True, lazy_update: bool = False):
+        """lazy_update: let the SGD update of the upper layers' matrices and of fc.W (HBM-bound, no consumer until the
+        next forward reaches them) run beside the NEXT step's forward recurrence kernels instead of at the end of this
+        step (zrb_set_lazy_update).  Same arithmetic; every Trainer entry point that reads parameters applies what is
+        pending first.  Only YOUR OWN reads or writes of the parameter tensors between two steps need `trainer.flush()`
+        before them (state_dict(), checkpoints, .cpu(), load_state_dict): until then `rnns.l>=1.weight_*` and `fc.W` hold
+        the previous values.
+        data_parallel: when torch.distributed is initialised, shard the batch over the ranks and all-reduce the
         gradients (default).  False = this process trains / evaluates its own replica alone (the sharded ensemble of
         BASELINE configs[4]: one model per GPU, no gradient exchange).
         keep_clipped_grads: after a step `.grad` holds coef * g as clip_grad_norm_ (main.py:115) leaves it.  The
@@ -79,6 +85,8 @@ class Trainer:
         self.model, self.B, self.T, self.dev = model, batch_size, seq_length, dev
         self.pg = process_group
         self._keep_clipped = bool(keep_clipped_grads)
+        self._lazy = bool(lazy_update) and model.engine == "tc"
+        self._pending = False          # lazy mode: a train step has run since the last flush
         self.world = (dist.get_world_size(process_group)
                       if data_parallel and dist.is_available() and dist.is_initialized() else 1)
         params = model.ordered_parameters()
@@ -89,12 +97,13 @@ class Trainer:
         # "nccl" = one torch.distributed all_reduce after backward
         # measured on 8xB200 (profiles/r01_bench_dp*.json): ce wins at 2 and 4 ranks (1.97 vs 2.23 ms, 2.10 vs
         # 2.39 ms), NCCL/NVLS alone wins at 8 (2.41 vs 2.55 ms: seven small peer copies per phase)
-        #   "nccl_ov" = bucket all-reduces on a communicator limited to a few CTAs, each started once the backward
-        #               recurrence kernel that runs beside it is resident (zrb_resident_flag), tail + sparse embedding
-        #               rows on the full communicator
+        # (A third transport -- bucket all-reduces on a few-CTA NCCL communicator, each held back with
+        # cuStreamWaitValue32 until the backward recurrence beside it is resident -- was built and HUNG on 2 GPUs: a
+        # stream blocked on a value that a kernel queued later on another stream will write can share a hardware work
+        # queue with that stream.  Removed; profiles/README.md has the note.)
         default = "ce" if self.world <= 4 else "nccl"
         self.transport = os.environ.get("ZRB_DP_TRANSPORT", default) if self.world > 1 else None
-        if self.transport not in (None, "ce", "nccl", "nccl_ov"):
+        if self.transport not in (None, "ce", "nccl"):
             raise ValueError(f"unknown ZRB_DP_TRANSPORT {self.transport!r}")
         self._dp = None
         if self.transport == "ce" and not self._ce_supported():
@@ -139,31 +148,21 @@ class Trainer:
         self._buckets.append((0, offs[1 + 4]))
         self._embed_end = offs[1]
         self._comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
-        # reduce buckets under the rest of backward (1) or all-reduce once after backward (0)
-        self.overlap = os.environ.get("ZRB_DP_OVERLAP", "0") == "1"
+        # (reducing finished buckets with NCCL underneath the rest of backward was measured slower in round 1 -- NCCL's
+        # channels evict part of the persistent recurrence grid, profiles/r01_bench_dp8_overlapped_buckets.json -- and
+        # was removed; the copy-engine transport is the one that overlaps)
         self._ctx_cached = None
         self._step_stream = None
         _ = self.ctx
         # single process: the fused step owns the gradient buffers -> touch only the window's embedding rows and take
         # the matrices' clip norm from the wgrad epilogues (mode 1).  Data parallel with the sparse embedding exchange
-        # ("ce", "nccl_ov"): rows-only embedding handling over ALL ranks' tokens (mode 2)
+        # (both transports): rows-only embedding handling over ALL ranks' tokens (mode 2)
         sparse_on = os.environ.get("ZRB_EMBED_SPARSE", "1") == "1"
-        self._embed_sparse = (1 if self.world == 1 else (2 if self.transport in ("ce", "nccl_ov") else 0)) if sparse_on else 0
+        self._embed_sparse = (1 if self.world == 1 else 2) if sparse_on else 0
         _lib.check(_lib.load().zrb_set_embed_sparse(self.ctx, self._embed_sparse))
         _lib.check(_lib.load().zrb_set_keep_clipped_grads(self.ctx, 1 if self._keep_clipped else 0))
-        self._pg_lo = None
-        if self.transport == "nccl_ov":
-            # a second communicator whose kernels take at most `ctas` SMs: they fit beside the 128-CTA backward
-            # recurrence (148 SMs) instead of evicting part of it (NCCL's default 24-32 channels do: rec_bwd 2x slower)
-            ctas = int(os.environ.get("ZRB_DP_NCCL_CTAS", "16"))
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.config.max_ctas = ctas
-            opts.config.min_ctas = min(ctas, 4)
-            self._pg_lo = dist.new_group(backend="nccl", pg_options=opts)
-            warm = torch.zeros(1 << 20, device=dev)
-            dist.all_reduce(warm, group=self._pg_lo)          # communicator set-up outside the timed steps
-            torch.cuda.synchronize(dev)
-        if self.transport in ("ce", "nccl_ov"):
+        _lib.check(_lib.load().zrb_set_lazy_update(self.ctx, 1 if self._lazy else 0))
+        if self.world > 1 and self._embed_sparse == 2:
             H, N = model.hidden_size, batch_size * seq_length
             self._rows = torch.zeros(N, H, device=dev)
             self._rows_all = torch.zeros(self.world * N, H, device=dev)
@@ -244,13 +243,21 @@ class Trainer:
             _lib.check(_lib.load().zrb_params_changed(c))
             _lib.check(_lib.load().zrb_set_embed_sparse(c, int(getattr(self, "_embed_sparse", 0))))
             _lib.check(_lib.load().zrb_set_keep_clipped_grads(c, 1 if self._keep_clipped else 0))
+            _lib.check(_lib.load().zrb_set_lazy_update(c, 1 if getattr(self, "_lazy", False) else 0))
             self._ctx_cached = c.value
         return c
+
+    def flush(self):
+        """Apply weight updates deferred by `lazy_update` now (no-op otherwise).  Call before reading parameter tensors
+        yourself between steps; train_step / eval_step / perplexity do not need it."""
+        _lib.check(_lib.load().zrb_flush_updates(self.ctx, self._stream()))
+        self._pending = False
 
     def params_changed(self):
         """Tell the library that parameter VALUES were changed outside it (model.load_state_dict, a manual edit):
         the fp16 operand images are rebuilt on the next step.  train_step / eval_step also detect in-place writes
         through the tensors' version counters, so calling this is only needed after writes torch cannot see."""
+        self.flush()
         _lib.check(_lib.load().zrb_params_changed(self.ctx))
         self._versions = self._param_versions()
 
@@ -260,6 +267,9 @@ class Trainer:
     def _check_versions(self):
         v = self._param_versions()
         if v != getattr(self, "_versions", None):
+            if getattr(self, "_versions", None) is not None and self._lazy and self._pending:
+                raise RuntimeError("parameters were modified outside the Trainer while lazy weight updates were still "
+                                   "pending: call trainer.flush() before reading or writing parameter tensors")
             _lib.check(_lib.load().zrb_params_changed(self.ctx))
             self._versions = v
 
@@ -307,15 +317,21 @@ class Trainer:
         self._check_versions()
         if self.world > 1 and self.transport == "ce":
             self._grads_ce(lib, x, y, T, B)
-        elif self.world > 1 and self.transport == "nccl_ov":
-            self._grads_nccl_ov(lib, x, y, T, B)
-        elif self.world > 1 and self.overlap:
-            self._grads_overlapped(lib, x, y, T, B)
         else:
+            # "nccl": backward in one piece (its weight-gradient GEMMs run beside the recurrence kernels), then ONE
+            # all-reduce of everything but the embedding table, whose gradient travels as rows (4 MB per rank
+            # instead of 60 MB dense) and is scattered deterministically on every rank
+            sparse = self.world > 1 and self._embed_sparse == 2
+            if sparse:
+                _lib.check(lib.zrb_set_embed_rows_out(self.ctx, _lib.ptr(self._rows)))
             _lib.check(lib.zrb_train_step_grads(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x),
                                                 _lib.ptr(y), T, B, C.byref(self._st), C.byref(self._st), self.seed,
                                                 self.step, _lib.ptr(self.loss), self._stream()))
-            if self.world > 1:
+            if sparse:
+                allreduce_sum_(self.flat_g[self._embed_end:], self.pg)
+                self._exchange_embedding_rows(lib, x, T, B)
+                _lib.check(lib.zrb_set_embed_rows_out(self.ctx, None))
+            elif self.world > 1:
                 allreduce_sum_(self.flat_g, self.pg)
         if self._dp is not None and self._keep_clipped:
             # the update rewrites g in place (coef * g) while peers may still be pulling this rank's reduced shards
@@ -324,6 +340,7 @@ class Trainer:
         _lib.check(lib.zrb_train_step_update(self.ctx, C.byref(self._ps), C.byref(self._gs), float(lr),
                                              float(max_norm), _lib.ptr(self.norm), self._stream()))
         self.step += 1
+        self._pending = True
         return self.loss, self.norm
 
     def _exchange_embedding_rows(self, lib, x, T, B):
@@ -334,75 +351,6 @@ class Trainer:
         dist.all_gather_into_tensor(self._ids_all[: self.world * N], x.reshape(-1), group=self.pg)
         _lib.check(lib.zrb_embed_scatter_rows(self.ctx, _lib.ptr(self.flat_g), _lib.ptr(self._ids_all),
                                               _lib.ptr(self._rows_all), self.world * N, self._stream()))
-
-    def _grads_nccl_ov(self, lib, x, y, T, B):
-        """Backward in phases; the buckets that finish early (fc, upper layers) are all-reduced on the few-CTA
-        communicator `_pg_lo` on a side stream.  Each of those all-reduces is held back (cuStreamWaitValue32 on the
-        flag the recurrence kernel publishes) until the backward recurrence launched right after the bucket completed
-        is fully resident, so NCCL's CTAs can only land on the SMs that kernel leaves idle.  The bucket that completes
-        with the end of backward (layer 0) and the embedding rows go through the full-width communicator."""
-        cur = torch.cuda.current_stream(self.dev)
-        comm = self._comm_stream
-        L = self.model.layer_num
-        flag, nxt = C.c_void_p(), C.c_uint32()
-
-        def reduce_bucket_gated(k):
-            lo, hi = self._buckets[k]
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            comm.wait_event(ev)
-            _lib.check(lib.zrb_resident_flag(self.ctx, C.byref(flag), C.byref(nxt)))
-            if nxt.value:
-                _lib.check(lib.zrb_stream_wait_value32(comm.cuda_stream, flag, nxt.value))
-            with torch.cuda.stream(comm):
-                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self._pg_lo)
-
-        _lib.check(lib.zrb_set_embed_rows_out(self.ctx, _lib.ptr(self._rows)))
-        _lib.check(lib.zrb_train_step_begin(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x), _lib.ptr(y),
-                                            T, B, C.byref(self._st), C.byref(self._st), self.seed, self.step,
-                                            _lib.ptr(self.loss), cur.cuda_stream))
-        reduce_bucket_gated(0)
-        k = 1
-        for l in range(L - 1, -1, -1):
-            _lib.check(lib.zrb_train_step_layer(self.ctx, C.byref(self._ps), C.byref(self._gs), l, cur.cuda_stream))
-            if l >= 1:
-                reduce_bucket_gated(k)
-                k += 1
-        lo, hi = self._buckets[-1]
-        allreduce_sum_(self.flat_g[self._embed_end:hi], self.pg)
-        self._exchange_embedding_rows(lib, x, T, B)
-        cur.wait_stream(comm)
-        _lib.check(lib.zrb_set_embed_rows_out(self.ctx, None))
-
-    def _grads_overlapped(self, lib, x, y, T, B):
-        """Backward in phases (zrb_train_step_begin / _layer); as soon as a bucket of the flat gradient
-        buffer is complete its SUM all-reduce is enqueued on a side stream, so the reduction of
-        fc / upper-layer gradients runs under the rest of backward.  Still one logical all-reduce
-        of the gradient buffer per step (ordered NCCL calls over disjoint slices)."""
-        cur = torch.cuda.current_stream(self.dev)
-        comm = self._comm_stream
-        L = self.model.layer_num
-
-        def reduce_bucket(k):
-            lo, hi = self._buckets[k]
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            comm.wait_event(ev)
-            with torch.cuda.stream(comm):
-                allreduce_sum_(self.flat_g[lo:hi], self.pg)
-
-        _lib.check(lib.zrb_train_step_begin(self.ctx, C.byref(self._ps), C.byref(self._gs), _lib.ptr(x), _lib.ptr(y),
-                                            T, B, C.byref(self._st), C.byref(self._st), self.seed, self.step,
-                                            _lib.ptr(self.loss), cur.cuda_stream))
-        reduce_bucket(0)
-        k = 1
-        for l in range(L - 1, -1, -1):
-            _lib.check(lib.zrb_train_step_layer(self.ctx, C.byref(self._ps), C.byref(self._gs), l, cur.cuda_stream))
-            if l >= 1:
-                reduce_bucket(k)
-                k += 1
-        reduce_bucket(len(self._buckets) - 1)
-        cur.wait_stream(comm)
 
     def train_step_host(self, x, y, lr, max_norm):
         """x, y: [T,B] int64 CPU tensors exactly as main.py:71-72 builds them.  Copies them to
@@ -430,6 +378,7 @@ class Trainer:
                                            float(lr), float(max_norm), C.c_void_p(self._hloss.data_ptr()),
                                            C.c_void_p(self._hloss.data_ptr() + 4), self._stream()))
         self.step += 1
+        self._pending = True
         return float(self._hloss[0]), float(self._hloss[1])
 
     # ---- main.py:91-94 --------------------------------------------------------------------
@@ -440,6 +389,7 @@ class Trainer:
         lib = _lib.load()
         T, B = x.shape
         self._check_versions()
+        self._pending = False          # zrb_eval_step applies what is pending before it reads the weights
         _lib.check(lib.zrb_eval_step(self.ctx, C.byref(self._ps), _lib.ptr(x), _lib.ptr(y), T, B,
                                      C.byref(self._st), C.byref(self._st), _lib.ptr(self.loss),
                                      _lib.ptr(self.tgt_prob) if want_probs else None, self._stream()))
