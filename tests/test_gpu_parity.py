@@ -5,8 +5,9 @@ Tolerances (stated per engine):
   simt  fp32 CUDA-core engine: differs from the fp32 reference only by summation order
         -> 5e-5 relative to the tensor's scale.
   tc    tcgen05 engine: fp16 operands (11-bit significand, the same as the TF32 the
-        reference's own cuDNN path uses on GPU), fp32 accumulation -> 4e-3 relative to the
-        tensor's scale on logits/states, 1.5e-2 on gradients ("Numerics").
+        reference's own cuDNN path uses on GPU), fp32 accumulation -> 1.2e-3 relative to the
+        tensor's scale on logits/states, 4e-3 on gradients and updated parameters: about three times
+        the largest error measured over the fixture cases ("Numerics").
 """
 import ctypes as C
 import os
@@ -21,7 +22,9 @@ from tests._golden import GOLDEN, STEP_CASES, StepCase
 pytestmark = pytest.mark.gpu
 
 ENGINES = os.environ.get("ZRB_TEST_ENGINES", "simt,tc").split(",")
-TOL = {"simt": dict(fwd=5e-5, grad=1e-4, loss=2e-5), "tc": dict(fwd=4e-3, grad=1.5e-2, loss=2e-3)}
+# tc: ~3x the largest error measured over all fixture cases on the B200 (profiles/r02_error_fixture_cases.json:
+# logits/states <= 3.6e-4, gradients / updated parameters <= 1.3e-3 of the tensor's scale)
+TOL = {"simt": dict(fwd=5e-5, grad=1e-4, loss=2e-5), "tc": dict(fwd=1.2e-3, grad=4e-3, loss=1e-3)}
 
 
 def _dev():
