@@ -3,10 +3,10 @@
 N=${1:-2}; STEPS=${2:-100}
 mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
-  timeout 900 python -m pytest tests/test_gpu_multi.py -q > gpurun_out/pytest_multi.log 2>&1; echo "pytest multi rc=$?" >> gpurun_out/pytest_multi.log; tail -8 gpurun_out/pytest_multi.log
+  timeout 420 python -m pytest tests/test_gpu_multi.py -q -x -s > gpurun_out/pytest_multi.log 2>&1; echo "pytest multi rc=$?" >> gpurun_out/pytest_multi.log; grep -E "^DP |passed|failed|Error|error" gpurun_out/pytest_multi.log | cut -c1-600 | tail -12
 fi
 for tr in ce nccl; do
-  ZRB_DP_TRANSPORT=$tr timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+  ZRB_DP_TRANSPORT=$tr timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
      bench.py --gpus $N --steps $STEPS --warmup 10 --no-cpu-baseline --no-gpu-baseline > gpurun_out/bench_dp${N}_$tr.json 2> gpurun_out/bench_dp${N}_$tr.err
   echo "dp$N $tr rc=$?"; tail -2 gpurun_out/bench_dp${N}_$tr.err | cut -c1-300
 done
