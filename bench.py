@@ -222,7 +222,9 @@ def run_ours(args, c, name):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # (NCCL_DEBUG is left alone: unset = silent; both VERSION and WARN make NCCL print its version line to stdout)
+        # stdout carries the ONE JSON line: whatever NCCL_DEBUG the box sets (VERSION and WARN both print "NCCL version
+        # ..." to stdout), send NCCL's own output to a file unless the caller already chose one
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/zrb_nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 

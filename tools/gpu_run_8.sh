@@ -15,7 +15,7 @@ import json
 for N in (8,4):
   for tr in ("nccl","ce"):
     try:
-        d=json.load(open(f"gpurun_out/bench_dp{N}_{tr}.json"))
+        d=json.loads([l for l in open(f"gpurun_out/bench_dp{N}_{tr}.json") if l.startswith("{")][0])
         print(N, tr, "ms/step", round(d["ms_per_step"],4), "tok/s", round(d["value"]), "e2e ms", round(d["e2e"]["ms_per_step"],4), d.get("dp_check",{}).get("replicas_identical"), d["roofline"]["class_ms_per_step"])
     except Exception as e: print(N, tr, "failed", e)
 PY

@@ -14,7 +14,7 @@ python - <<PY
 import json
 for tr in ("ce","nccl"):
     try:
-        d=json.load(open("gpurun_out/bench_dp${N}_%s.json" % tr))
+        d=json.loads([l for l in open("gpurun_out/bench_dp${N}_%s.json" % tr) if l.startswith("{")][0])
         print(tr, "ms/step", round(d["ms_per_step"],4), "tok/s", round(d["value"]), "e2e ms", round(d["e2e"]["ms_per_step"],4), d.get("dp_check"), d["roofline"]["class_ms_per_step"])
     except Exception as e: print(tr, "failed", e)
 PY
