@@ -68,3 +68,19 @@ def test_custom_gate_permutation_is_involution():
     a = torch.arange(8.0).view(8, 1)
     assert _ifon_to_ifgo(a).view(-1).tolist() == [0, 1, 2, 3, 6, 7, 4, 5]
     assert torch.equal(_ifon_to_ifgo(_ifon_to_ifgo(a)), a)
+
+
+def test_ptb_id_fixture_is_consistent_with_the_reference_slice():
+    """tests/golden/ptb_ids.npz (minted by make_ptb_ids.py with the vocabulary rule of main.py:44-59) must agree with the
+    ids make_golden.py took from the same text through its own restatement of that rule (first 1500 validation tokens),
+    have the reference's corpus sizes and '\\n' as id 0 once per line."""
+    z = np.load(os.path.join(GOLDEN, "ptb_ids.npz"))
+    s = np.load(os.path.join(GOLDEN, "perplexity_ptb_slice.npz"))
+    assert int(z["vocab_size"]) == 10000
+    assert (z["train"].size, z["valid"].size, z["test"].size) == (929589, 73760, 82430)
+    assert z["train"].dtype == np.int16 and int(z["train"].max()) == 9999 and int(z["train"].min()) == 0
+    np.testing.assert_array_equal(z["valid"][:1500].astype(np.int64), s["ids"].reshape(-1).astype(np.int64))
+    assert (int((z["train"] == 0).sum()), int((z["valid"] == 0).sum()), int((z["test"] == 0).sum())) == (42068, 3370, 3761)
+    # the re-batching the recipes use: 1327 windows of [35, 20] for Medium / Large, 2323 of [20, 20] for Small
+    assert len(zaremba_b200.minibatch(z["train"].astype(np.int64).reshape(-1, 1), 20, 35)) == 1327
+    assert len(zaremba_b200.minibatch(z["train"].astype(np.int64).reshape(-1, 1), 20, 20)) == 2323
