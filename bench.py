@@ -204,7 +204,7 @@ def run_reference(args, c, name):
             "config": bench_config(name, c, max(1, args.gpus), "torch CPU (oneDNN)", None, "host CPU"),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, c, name):
@@ -222,9 +222,6 @@ def run_ours(args, c, name):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries the ONE JSON line: whatever NCCL_DEBUG the box sets (VERSION and WARN both print "NCCL version
-        # ..." to stdout), send NCCL's own output to a file unless the caller already chose one
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/zrb_nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -363,12 +360,29 @@ def run_ours(args, c, name):
         line["e2e"]["vs_gpu_baseline"] = line["e2e"]["value"] / gb["value"]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_port_leg(c, args.cpu_budget)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything libraries print while the bench runs (NCCL's
+    "NCCL version ..." banner, for one) was diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # fd 1 -> stderr for the duration of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
