@@ -262,6 +262,22 @@ int  zrb_prof_rec_trace(zrb_ctx* ctx, int64_t* h_out, int32_t max_entries);
 
 /* ---- building blocks, exported for unit tests and profiling ------------------------ */
 
+/* ONE recurrent layer over the window through the persistent recurrence kernels alone (model.py:48-55, the nn.LSTM(H,H)
+ * call of model.py:107; SURVEY 8b's zrb_lstm_layer_fwd / _bwd): input GEMM + weight-stationary recurrence, no dropout
+ * (the caller applies it, as model.py:105,108 do).  Tensor-core engine only, shapes the persistent kernels accept
+ * (B <= 32).  Gate row blocks (i, f, g, o).
+ *   x [T*B,H] fp32 layer input; h0, c0 [B,H]; y [T*B,H] fp32 = h_t; hT, cT [B,H] final state (may be NULL)
+ * The activations stay in the context for zrb_lstm_layer_bwd:
+ *   dy [T*B,H] = d loss / d y (no gradient flows into hT / cT: the reference detaches the carried state, main.py:110)
+ *   dx [T*B,H] (or NULL), dw_ih, dw_hh [4H,H], db_ih, db_hh [4H] : OVERWRITTEN
+ * These calls borrow the context's layer-0 workspace: model-level weight images are rebuilt at the next model-level call. */
+int  zrb_lstm_layer_fwd(zrb_ctx* ctx, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                        const float* x, int32_t T, int32_t B, const float* h0, const float* c0, float* y, float* hT,
+                        float* cT, void* stream);
+int  zrb_lstm_layer_bwd(zrb_ctx* ctx, const float* dy, float* dx, float* dw_ih, float* dw_hh, float* db_ih,
+                        float* db_hh, void* stream);
+
+
 /* C[M,N] = alpha * A[M,K] * op(B) + beta * C  in fp32 on CUDA cores.
  * transB != 0: B is [N,K] (C = A * B^T);  transB == 0: B is [K,N].
  * transA != 0: A is stored [K,M]. */

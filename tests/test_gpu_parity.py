@@ -408,6 +408,55 @@ def test_perplexity_and_ensemble_on_ptb_slice(engine):
     assert abs(ens - float(z["ens_loss"])) < TOL[engine]["loss"] * abs(float(z["ens_loss"]))
 
 
+@pytest.mark.parametrize("H,T,B", [(1500, 35, 20), (650, 35, 20), (200, 20, 20), (96, 5, 7)])
+def test_lstm_layer_unit_abi_against_oracle(H, T, B):
+    """zrb_lstm_layer_fwd / zrb_lstm_layer_bwd: ONE recurrent layer through the persistent recurrence kernels alone, at
+    the exact per-layer shapes of BASELINE configs[0..2] (SURVEY 8b's unit-level entry points), against the fp64
+    restatement of model.py:48-55 and of its autograd (oracle lstm_layer_fwd / lstm_layer_bwd).  Non-zero incoming state.
+    Tolerance: 1.2e-3 of each tensor's scale forward, 2.5e-3 backward (~3x the measured error of the tcgen05 engine)."""
+    import zaremba_b200
+    from zaremba_b200 import _lib
+    lib = _lib.load()
+    m = zaremba_b200.Model(16, H, 1, 0.0, 0.05, engine="tc").to(_dev())
+    ctx = m._context(T, B)
+    rng = np.random.default_rng(H + T)
+    w = 0.04 if H >= 1000 else 0.08
+    W_ih, W_hh = rng.uniform(-w, w, size=(4 * H, H)), rng.uniform(-w, w, size=(4 * H, H))
+    b_ih, b_hh = rng.uniform(-w, w, size=4 * H), rng.uniform(-w, w, size=4 * H)
+    x = rng.normal(size=(T, B, H)) * 0.5
+    h0, c0 = rng.uniform(-0.5, 0.5, size=(B, H)), rng.uniform(-1.0, 1.0, size=(B, H))
+    dy = rng.normal(size=(T, B, H)) * 0.1
+    dev = lambda a: torch.tensor(a, dtype=torch.float32).contiguous().to(_dev())
+    d = {k: dev(v) for k, v in dict(W_ih=W_ih, W_hh=W_hh, b_ih=b_ih, b_hh=b_hh, x=x, h0=h0, c0=c0, dy=dy).items()}
+    y, hT, cT = torch.empty(T * B, H, device=_dev()), torch.empty(B, H, device=_dev()), torch.empty(B, H, device=_dev())
+    _lib.check(lib.zrb_lstm_layer_fwd(ctx, _lib.ptr(d["W_ih"]), _lib.ptr(d["W_hh"]), _lib.ptr(d["b_ih"]), _lib.ptr(d["b_hh"]),
+                                      _lib.ptr(d["x"]), T, B, _lib.ptr(d["h0"]), _lib.ptr(d["c0"]), _lib.ptr(y), _lib.ptr(hT),
+                                      _lib.ptr(cT), None))
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)          # the values the device actually received
+    ys, h_ref, c_ref, cache = O.lstm_layer_fwd(f32(x), f32(h0), f32(c0), f32(W_ih), f32(W_hh), f32(b_ih), f32(b_hh))
+    _scale_close(y.cpu().numpy().reshape(T, B, H), ys, 1.2e-3, f"layer H={H} y")
+    _scale_close(hT.cpu().numpy(), h_ref, 1.2e-3, f"layer H={H} hT")
+    _scale_close(cT.cpu().numpy(), c_ref, 1.2e-3, f"layer H={H} cT")
+    dx, dWi, dWh = torch.empty(T * B, H, device=_dev()), torch.empty(4 * H, H, device=_dev()), torch.empty(4 * H, H, device=_dev())
+    dbi, dbh = torch.empty(4 * H, device=_dev()), torch.empty(4 * H, device=_dev())
+    _lib.check(lib.zrb_lstm_layer_bwd(ctx, _lib.ptr(d["dy"]), _lib.ptr(dx), _lib.ptr(dWi), _lib.ptr(dWh), _lib.ptr(dbi),
+                                      _lib.ptr(dbh), None))
+    dx_r, dWi_r, dWh_r, db_r = O.lstm_layer_bwd(f32(dy), cache, f32(x), f32(W_ih), f32(W_hh))
+    _scale_close(dx.cpu().numpy().reshape(T, B, H), dx_r, 2.5e-3, f"layer H={H} grad dx")
+    _scale_close(dWi.cpu().numpy(), dWi_r, 2.5e-3, f"layer H={H} grad dW_ih")
+    _scale_close(dWh.cpu().numpy(), dWh_r, 2.5e-3, f"layer H={H} grad dW_hh")
+    _scale_close(dbi.cpu().numpy(), db_r, 2.5e-3, f"layer H={H} grad db_ih")
+    assert torch.equal(dbi, dbh)
+    # call order is enforced, and the model-level path still works after the unit-level calls borrowed its workspace
+    assert lib.zrb_lstm_layer_bwd(ctx, _lib.ptr(d["dy"]), _lib.ptr(dx), _lib.ptr(dWi), _lib.ptr(dWh), _lib.ptr(dbi),
+                                  _lib.ptr(dbh), None) == -3
+    xtok = torch.zeros(T, B, dtype=torch.long)
+    with torch.no_grad():
+        s1, _ = m(xtok, m.state_init(B))
+        s2, _ = m(xtok, m.state_init(B))
+    assert torch.equal(s1, s2) and torch.isfinite(s1).all()
+
+
 def test_error_paths():
     """Reference-like error behaviour: bad shapes / call order raise instead of corrupting memory."""
     import zaremba_b200

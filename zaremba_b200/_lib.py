@@ -85,6 +85,8 @@ _SIGNATURES = {
     "zrb_dp_begin_step": (C.c_int, [_vp, _vp]),
     "zrb_dp_finish_step": (C.c_int, [_vp, _vp]),
     "zrb_dp_allreduce_bucket": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _vp]),
+    "zrb_lstm_layer_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "zrb_lstm_layer_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "zrb_prof_enable": (C.c_int, [_vp, C.c_int32]),
     "zrb_prof_read": (C.c_int, [_vp, _vp, _vp]),
     "zrb_prof_rec_trace": (C.c_int, [_vp, _vp, C.c_int32]),

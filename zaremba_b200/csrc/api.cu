@@ -383,6 +383,23 @@ int zrb_train_step_host(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
     return ZRB_OK;
 }
 
+int zrb_lstm_layer_fwd(zrb_ctx* c, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                       const float* x, int32_t T, int32_t B, const float* h0, const float* c0, float* y, float* hT,
+                       float* cT, void* stream) {
+    ZRB_REQUIRE(c && w_ih && w_hh && b_ih && b_hh && x && h0 && c0 && y, "null argument");
+    ZRB_TRY(check_shapes(c, T, B));
+    ZRB_REQUIRE(c->cfg.engine == ZRB_ENGINE_TC, "zrb_lstm_layer_fwd is an entry point of the tensor-core engine");
+    ZRB_REQUIRE(h0 != hT && c0 != cT, "the unit-level entry point does not alias states");
+    return tc_layer_fwd(c, w_ih, w_hh, b_ih, b_hh, x, T, B, h0, c0, y, hT, cT, (cudaStream_t)stream);
+}
+
+int zrb_lstm_layer_bwd(zrb_ctx* c, const float* dy, float* dx, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                       void* stream) {
+    ZRB_REQUIRE(c && dy && dw_ih && dw_hh && db_ih && db_hh, "null argument");
+    ZRB_REQUIRE(c->cfg.engine == ZRB_ENGINE_TC, "zrb_lstm_layer_bwd is an entry point of the tensor-core engine");
+    return tc_layer_bwd(c, dy, dx, dw_ih, dw_hh, db_ih, db_hh, (cudaStream_t)stream);
+}
+
 int zrb_prof_enable(zrb_ctx* c, int32_t on) {
     ZRB_REQUIRE(c, "null ctx");
     c->prof_on = on != 0;

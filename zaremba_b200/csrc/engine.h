@@ -37,6 +37,7 @@ struct zrb_ctx {
     int T = 0, B = 0, train = 0;
     uint64_t seed = 0, step = 0;
     bool have_fwd = false;
+    bool layer_fwd_ok = false;             // zrb_lstm_layer_fwd ran and its activations are still in slot 0
     bool explicit_masks_set = false;
     const uint8_t* explicit_masks[ZRB_MAX_LAYERS + 1] = {};
     int64_t weights_version = 1;           // bumped whenever parameter values change
@@ -97,7 +98,11 @@ int tc_train_step_begin(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
 int tc_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, int l, cudaStream_t s);
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries);
 int tc_flush_updates(zrb_ctx* c, cudaStream_t s);   // apply deferred weight updates now (zrb_set_lazy_update)
-bool tc_persistent_bwd(const zrb_ctx* c);   // the persistent backward recurrence kernel is in use for this context
+bool tc_persistent_bwd(const zrb_ctx* c);
+int tc_layer_fwd(zrb_ctx* c, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* x,
+                 int T, int B, const float* h0, const float* c0, float* y, float* hT, float* cT, cudaStream_t s);
+int tc_layer_bwd(zrb_ctx* c, const float* dy, float* dx, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                 cudaStream_t s);   // the persistent backward recurrence kernel is in use for this context
 int tc_update(zrb_ctx* c, const zrb_params* p, const TensorList& tl, float lr, float max_norm, float* norm_out,
               cudaStream_t s);
 

@@ -463,6 +463,70 @@ int tc_train_step_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* g, in
 
 bool tc_persistent_bwd(const zrb_ctx* c) { return c->tc && c->tc->bplan.ok; }
 
+// ---- unit-level entry points: ONE recurrent layer through the persistent kernels (zrb_lstm_layer_fwd / _bwd) --------
+// They borrow layer slot 0 of the context (images, activations) and leave the model-level weight images stale, so the
+// next model-level call repacks.
+int tc_layer_fwd(zrb_ctx* c, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* x,
+                 int T, int B, const float* h0, const float* c0, float* y, float* hT, float* cT, cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, N = T * B, Hp = t->Hp;
+    if (!t->fplan.ok || !t->bplan.ok) {
+        set_error("zrb_lstm_layer_fwd needs the persistent recurrence kernels (shape H=%d B=%d does not fit them)", H, B);
+        return ZRB_E_INVALID;
+    }
+    ZRB_TRY(tc_flush_updates(c, s));
+    c->T = T; c->B = B; c->train = 0;
+    t->packed_version = 0;                       // slot 0 is about to hold this call's weights
+    ZRB_TRY(convert_pad_f16(w_ih, H, t->w_ih_h[0], Hp, 4 * H, H, 1.f, s));
+    ZRB_TRY(pack_whh_fwd(w_hh, t->w_img_f[0], H, t->fplan, s));
+    ZRB_TRY(pack_whh_bwd(w_hh, t->w_img_b[0], H, t->bplan, s));
+    ZRB_TRY(convert_pad_f16(x, H, t->x_h[0], Hp, N, H, 1.f, s));
+    FwdPrep fp = {};
+    fp.in_h[0] = h0; fp.in_c[0] = c0; fp.h0s[0] = c->h0s[0]; fp.c0s[0] = c->c0s[0];
+    fp.hprev_h[0] = t->hprev_h[0]; fp.h0_img[0] = t->h0_img[0];
+    fp.x = nullptr; fp.x_saved = nullptr;
+    fp.L = 1; fp.B = B; fp.H = H; fp.Hp = Hp; fp.GB = t->fplan.GBi; fp.Kc = t->fplan.Kc; fp.N = 0;
+    ZRB_TRY(fwd_prep(fp, s));
+    ZRB_TRY(gemm_f16_tc(t->x_h[0], Hp, 0, t->w_ih_h[0], Hp, 0, c->gates[0], 4 * H, N, 4 * H, H, 1.f, b_ih, 0, s, nullptr, b_hh));
+    const unsigned int arrivals = (unsigned int)T * (unsigned int)t->fplan.nCTA;
+    if (t->cnt_f > 0xF0000000u - arrivals) {
+        ZRB_CUDA(cudaMemsetAsync(t->counter, 0, sizeof(unsigned int), s));
+        t->cnt_f = 0;
+    }
+    MaskSrc m = make_mask_src(nullptr, 0, 0, 0, 0.f, 0);    // no dropout at this level: the caller applies it (model.py:105,108)
+    ZRB_TRY(lstm_rec_fwd(t->fplan, t->w_img_f[0], t->h0_img[0], t->h_img, c->gates[0], c->c0s[0], c->cst[0], hT, cT,
+                         t->hprev_h[0], t->x_h[1], t->counter, t->cnt_f, T, B, H, Hp, m, s, nullptr, y));
+    t->cnt_f += arrivals;
+    c->have_fwd = false;                         // a model-level backward must not follow this
+    c->layer_fwd_ok = true;
+    return ZRB_OK;
+}
+
+int tc_layer_bwd(zrb_ctx* c, const float* dy, float* dx, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                 cudaStream_t s) {
+    zrb_tc_state* t = c->tc;
+    const int H = c->cfg.hidden, T = c->T, B = c->B, N = T * B, Hp = t->Hp, G4p = t->G4p;
+    if (!c->layer_fwd_ok) {
+        set_error("zrb_lstm_layer_bwd without a preceding zrb_lstm_layer_fwd");
+        return ZRB_E_STATE;
+    }
+    const unsigned int arrivals = (unsigned int)T * (unsigned int)t->bplan.nCTA;
+    if (t->cnt_b > 0xF0000000u - arrivals) {
+        ZRB_CUDA(cudaMemsetAsync(t->counter + 32, 0, sizeof(unsigned int), s));
+        t->cnt_b = 0;
+    }
+    MaskSrc m = make_mask_src(nullptr, 0, 0, 0, 0.f, 0);
+    ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[0], t->g_img, dy, c->gates[0], c->cst[0], c->c0s[0], t->dG_h, t->counter + 32,
+                         t->cnt_b, T, B, H, G4p, m, s, nullptr, db_ih, db_hh, c->resident_flag, ++c->resident_seq, c->dG));
+    t->cnt_b += arrivals;
+    const float inv = 1.f / kGradScale;
+    if (dx) ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 0, t->w_ih_h[0], Hp, 1, dx, H, N, H, 4 * H, inv, nullptr, 0, s));
+    ZRB_TRY(gemm_f16_tc(t->dG_h, G4p, 1, t->x_h[0], Hp, 1, dw_ih, H, 4 * H, H, N, inv, nullptr, 0, s, nullptr, nullptr, false,
+                        t->hprev_h[0], dw_hh, nullptr));
+    c->layer_fwd_ok = false;
+    return ZRB_OK;
+}
+
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries) {
     if (!c->tc || !c->tc->trace) { set_error("set ZRB_REC_TRACE=1 before creating the context"); return ZRB_E_STATE; }
     int n = 2 * c->cfg.max_seq * 8;

@@ -53,10 +53,12 @@ struct RecFwdArgs {
     float* c_last;            // [B,H] or null
     __half* hprev_h;          // [N+B,Hp] row-major, rows B.. written here
     __half* y_h;              // [N,Hp] row-major dropout(h)
+    float* h_f32;             // or null: [N,H] fp32 h_t (the unit-level entry point zrb_lstm_layer_fwd returns it)
     unsigned int* counter;    // grid barrier: never reset, `base` is its value when this launch starts
     unsigned int base;
     int T, B, H, Hp, U, G, GB, Kc, nCTA;
     int KcS, GBi;             // K chunks per CTA (Kc / KS); 8-row batch groups of the operand image (GB, or 4 when N = 32)
+    int reorder;              // K-split drain order: partner's rows first (A/B switch ZRB_REC_REORDER=0)
     MaskSrc m;
     long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
 };
@@ -203,9 +205,19 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
                 // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
                 // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
-                for (int task = warp; task < 4 * a.GBi; task += kRecEpiWarps) {
-                    const int quad = task & 3, c0 = (task >> 2) * 8;
-                    if (SPLIT && 32 * quad >= rows_pair) continue;        // M = 128: row i sits in lane i; padding quadrant
+                // K-split: only the lane quadrants that hold real rows are tasks, and they are visited so that the rows
+                // bound for the PARTNER leave first (rank 0 owns the low rows: quadrants top-down; rank 1: bottom-up) --
+                // the partner's rows are then in flight while this CTA drains the rows it keeps
+                const int nq = SPLIT ? (rows_pair + 31) / 32 : 4;
+                for (int task = warp; task < nq * a.GBi; task += kRecEpiWarps) {
+                    int quad, c0;
+                    if (SPLIT) {
+                        const int qi = task / a.GBi;
+                        quad = (rank == 0 && a.reorder) ? nq - 1 - qi : qi;
+                        c0 = (task - qi * a.GBi) * 8;
+                    } else {
+                        quad = task & 3; c0 = (task >> 2) * 8;
+                    }
                     uint32_t v[kRecMmaWarps][8];
                     const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
 #pragma unroll
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 a.hprev_h[((size_t)B + n) * a.Hp + j] = __float2half_rn(o_h[k]);
                 float y = o_h[k] * mask_mul1(a.m, (uint64_t)n * H + j, n_total);
                 a.y_h[n * a.Hp + j] = __float2half_rn(y);
+                if (a.h_f32) a.h_f32[n * H + j] = o_h[k];
                 if (t == a.T - 1) {
                     if (a.h_last) a.h_last[(size_t)b * H + j] = o_h[k];
                     if (a.c_last) a.c_last[(size_t)b * H + j] = creg[k];
@@ -411,7 +424,7 @@ int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
 int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
                  const float* c0, float* cst, float* h_last, float* c_last, __half* hprev_h, __half* y_h,
                  unsigned int* counter, unsigned int counter_base, int T, int B, int H, int Hp, MaskSrc m, cudaStream_t s,
-                 long long* trace) {
+                 long long* trace, float* h_f32) {
     static bool attr[64] = {};   // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
@@ -423,9 +436,11 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
     }
     RecFwdArgs a;
     a.w_img = w_img; a.h0_img = h0_img; a.h_img = h_img; a.base = counter_base; a.gates = gates; a.c0 = c0; a.cst = cst; a.h_last = h_last; a.c_last = c_last;
-    a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter;
+    a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter; a.h_f32 = h_f32;
     a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
     a.KcS = p.KcS; a.GBi = p.GBi;
+    static const bool no_reorder = getenv("ZRB_REC_REORDER") != nullptr && getenv("ZRB_REC_REORDER")[0] == '0';
+    a.reorder = no_reorder ? 0 : 1;
     a.trace = trace;
     if (p.KS == 1) {
         void* args[] = {&a};

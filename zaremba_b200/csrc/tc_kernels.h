@@ -42,7 +42,7 @@ int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
 int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
                  const float* c0, float* cst, float* h_last, float* c_last, __half* hprev_h, __half* y_h,
                  unsigned int* counter, unsigned int counter_base, int T, int B, int H, int Hp, MaskSrc m, cudaStream_t s,
-                 long long* trace = nullptr);
+                 long long* trace = nullptr, float* h_f32 = nullptr);   // h_f32: optional [N,H] fp32 copy of h_t
 // Everything the forward needs from the incoming state and tokens in ONE launch (it replaced 9: five device
 // copies, two fp16 conversions, two image packs): h0s/c0s = copies of the incoming (h, c) (the caller may pass
 // the same buffers for the outgoing state), hprev_h rows [0,B) = half(h0) with zeroed pad columns, h0_img = the
