@@ -41,7 +41,6 @@ struct RecBwdArgs {
     unsigned int base;
     int T, B, H, G4p, U, G, GB, Kc, nCTA;
     int KcS, GBi;             // K chunks per CTA (Kc / S); 8-row batch groups of the dG images (GB, or 4 when N = 32)
-    int reorder;              // S = 2 drain order: other CTAs' rows first (A/B switch ZRB_REC_REORDER=0)
     MaskSrc m;
     long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
 };
@@ -250,19 +249,10 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
                     // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
                     // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
-                    // S = 2: only the lane quadrants that hold real rows are tasks, visited in ring order starting behind
-                    // the quadrant that holds this CTA's own units, so the rows bound for the other CTAs leave first
-                    const int nq = S == 2 ? (UC + 31) / 32 : 4;
-                    const int my_q = ((int)rank * a.U + a.U / 2) / 32;
-                    for (int task = warp; task < nq * a.GBi; task += kRecEpiWarps) {
-                        int quad, c0;
-                        if (S == 2) {
-                            const int qi = task / a.GBi;
-                            quad = a.reorder ? (my_q + 1 + qi) % nq : qi;
-                            c0 = (task - qi * a.GBi) * 8;
-                        } else {
-                            quad = task & 3; c0 = (task >> 2) * 8;
-                        }
+                    // (task -> lane quadrant is fixed by the warp index: a warp reads only TMEM lanes [32*(warp%4), +32))
+                    for (int task = warp; task < 4 * a.GBi; task += kRecEpiWarps) {
+                        const int quad = task & 3, c0 = (task >> 2) * 8;
+                        if (S == 2 && 32 * quad >= UC) continue;          // M = 128: row i sits in lane i; padding quadrant
                         uint32_t v[kRecMmaWarps][8];
                         const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
 #pragma unroll
@@ -594,8 +584,6 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     a.counter = counter; a.db1 = db1; a.db2 = db2; a.db_scratch = db_scratch; a.res_flag = resident_flag; a.res_value = resident_value;
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     a.KcS = p.KcS; a.GBi = p.GBi;
-    static const bool no_reorder = getenv("ZRB_REC_REORDER") != nullptr && getenv("ZRB_REC_REORDER")[0] == '0';
-    a.reorder = no_reorder ? 0 : 1;
     return p.KS == 2 ? launch_rec_bwd<2>(p, a, s) : launch_rec_bwd<1>(p, a, s);
 }
 

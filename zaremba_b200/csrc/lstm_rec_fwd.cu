@@ -58,7 +58,6 @@ struct RecFwdArgs {
     unsigned int base;
     int T, B, H, Hp, U, G, GB, Kc, nCTA;
     int KcS, GBi;             // K chunks per CTA (Kc / KS); 8-row batch groups of the operand image (GB, or 4 when N = 32)
-    int reorder;              // K-split drain order: partner's rows first (A/B switch ZRB_REC_REORDER=0)
     MaskSrc m;
     long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
 };
@@ -205,19 +204,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
                 // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
                 // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
-                // K-split: only the lane quadrants that hold real rows are tasks, and they are visited so that the rows
-                // bound for the PARTNER leave first (rank 0 owns the low rows: quadrants top-down; rank 1: bottom-up) --
-                // the partner's rows are then in flight while this CTA drains the rows it keeps
-                const int nq = SPLIT ? (rows_pair + 31) / 32 : 4;
-                for (int task = warp; task < nq * a.GBi; task += kRecEpiWarps) {
-                    int quad, c0;
-                    if (SPLIT) {
-                        const int qi = task / a.GBi;
-                        quad = (rank == 0 && a.reorder) ? nq - 1 - qi : qi;
-                        c0 = (task - qi * a.GBi) * 8;
-                    } else {
-                        quad = task & 3; c0 = (task >> 2) * 8;
-                    }
+                // (A warp can only read the TMEM lane quadrant (warp % 4): task -> quadrant is fixed by the warp index, so the
+                // drain order ACROSS quadrants cannot be chosen -- an attempt to send the partner's rows first broke this.)
+                for (int task = warp; task < 4 * a.GBi; task += kRecEpiWarps) {
+                    const int quad = task & 3, c0 = (task >> 2) * 8;
+                    if (SPLIT && 32 * quad >= rows_pair) continue;        // M = 128: row i sits in lane i; padding quadrant
                     uint32_t v[kRecMmaWarps][8];
                     const uint32_t base = tmem_d + ((uint32_t)(32 * quad) << 16) + c0;
 #pragma unroll
@@ -439,8 +430,6 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
     a.hprev_h = hprev_h; a.y_h = y_h; a.counter = counter; a.h_f32 = h_f32;
     a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
     a.KcS = p.KcS; a.GBi = p.GBi;
-    static const bool no_reorder = getenv("ZRB_REC_REORDER") != nullptr && getenv("ZRB_REC_REORDER")[0] == '0';
-    a.reorder = no_reorder ? 0 : 1;
     a.trace = trace;
     if (p.KS == 1) {
         void* args[] = {&a};
