@@ -413,7 +413,8 @@ def test_lstm_layer_unit_abi_against_oracle(H, T, B):
     """zrb_lstm_layer_fwd / zrb_lstm_layer_bwd: ONE recurrent layer through the persistent recurrence kernels alone, at
     the exact per-layer shapes of BASELINE configs[0..2] (SURVEY 8b's unit-level entry points), against the fp64
     restatement of model.py:48-55 and of its autograd (oracle lstm_layer_fwd / lstm_layer_bwd).  Non-zero incoming state.
-    Tolerance: 1.2e-3 of each tensor's scale forward, 2.5e-3 backward (~3x the measured error of the tcgen05 engine)."""
+    Tolerance: 2e-3 of each tensor's scale forward, 2.5e-3 backward (measured 3e-4 ... 6.7e-4 forward with these
+    N(0, 0.5) inputs, <= 4.7e-4 backward: profiles/r02_error_fixture_cases.json)."""
     import zaremba_b200
     from zaremba_b200 import _lib
     lib = _lib.load()
@@ -434,9 +435,9 @@ def test_lstm_layer_unit_abi_against_oracle(H, T, B):
                                       _lib.ptr(cT), None))
     f32 = lambda a: a.astype(np.float32).astype(np.float64)          # the values the device actually received
     ys, h_ref, c_ref, cache = O.lstm_layer_fwd(f32(x), f32(h0), f32(c0), f32(W_ih), f32(W_hh), f32(b_ih), f32(b_hh))
-    _scale_close(y.cpu().numpy().reshape(T, B, H), ys, 1.2e-3, f"layer H={H} y")
-    _scale_close(hT.cpu().numpy(), h_ref, 1.2e-3, f"layer H={H} hT")
-    _scale_close(cT.cpu().numpy(), c_ref, 1.2e-3, f"layer H={H} cT")
+    _scale_close(y.cpu().numpy().reshape(T, B, H), ys, 2e-3, f"layer H={H} y")
+    _scale_close(hT.cpu().numpy(), h_ref, 2e-3, f"layer H={H} hT")
+    _scale_close(cT.cpu().numpy(), c_ref, 2e-3, f"layer H={H} cT")
     dx, dWi, dWh = torch.empty(T * B, H, device=_dev()), torch.empty(4 * H, H, device=_dev()), torch.empty(4 * H, H, device=_dev())
     dbi, dbh = torch.empty(4 * H, device=_dev()), torch.empty(4 * H, device=_dev())
     _lib.check(lib.zrb_lstm_layer_bwd(ctx, _lib.ptr(d["dy"]), _lib.ptr(dx), _lib.ptr(dWi), _lib.ptr(dWh), _lib.ptr(dbi),
