@@ -281,9 +281,12 @@ def run_ours(args, c, name):
         dp_check = {"param_checksum_max_minus_min": [int(v) for v in (hi - lo).tolist()],
                     "replicas_identical": bool((hi == lo).all().item()), "after_steps": K + W}
     # the same step in the mode that leaves coef * g in .grad like clip_grad_norm_ (main.py:115) does
+    was_keep = tr._keep_clipped
+    tr._keep_clipped = True                      # (also arms the copy-engine transport's wait for the peers' pulls)
     _lib.check(lib.zrb_set_keep_clipped_grads(tr.ctx, 1))
     keep_ms, _, _ = timed_region(lambda x, y: tr.train_step(x, y, c["lr"], c["clip"]), dev_batches)
-    _lib.check(lib.zrb_set_keep_clipped_grads(tr.ctx, 1 if tr._keep_clipped else 0))
+    tr._keep_clipped = was_keep
+    _lib.check(lib.zrb_set_keep_clipped_grads(tr.ctx, 1 if was_keep else 0))
     # 2) end to end through the host-buffer call (wall clock: H2D, step, D2H of the loss each step)
     tr.reset_states()
     _, e2e_wall_ms, _ = timed_region(lambda x, y: tr.train_step_host(x, y, c["lr"], c["clip"]), host_batches)
