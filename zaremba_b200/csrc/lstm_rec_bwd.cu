@@ -1,21 +1,25 @@
-// Persistent LSTM recurrence, backward, one launch per layer (sm_100a, clusters of 4 CTAs).
+// Persistent LSTM recurrence, backward, one launch per layer (sm_100a, thread-block clusters).
 //
 //   for t in T-1..0:  dh_t = mask * dY_t + dG_{t+1} * W_hh ;  cell backward -> dG_t, dc      
 //
 // The contraction dG_{t+1}[B,4H] * W_hh[4H,H] runs over the 4H gate rows.  A CTA that owned only a few
-// hidden units would fill 16 of the 64 rows of the smallest tcgen05 tile, so instead a CLUSTER of four
-// CTAs owns UC = 4U units and splits the contraction by gate: CTA rank r holds the fp16 slice
-// W_hh[r*H:(r+1)*H, units]^T  (UC x H, K-major, canonical no-swizzle UMMA layout) resident in shared
-// memory and multiplies it with gate r's block of dG_{t+1}.  The four partial products D_r[UC x B]
-// are exchanged through distributed shared memory as a reduce-scatter: every CTA stages its accumulators
-// in its own shared memory, announces it with a cluster-scope mbarrier (remote
-// mbarrier.arrive.release.cluster), and then PULLS, for the U units whose cell math it owns, the four
-// CTAs' partials with batched ld.shared::cluster loads.  (Pushing rows into the owners' shared memory
-// with st.shared::cluster was measured 5% slower.)  dc lives in registers for the whole window.
+// hidden units would fill 16 of the 64 rows of the smallest tcgen05 tile, so a CLUSTER owns UC units and
+// splits the contraction between its CTAs; every CTA keeps its slice W_hh[rows of its share, units]^T
+// (K-major, canonical no-swizzle UMMA layout, ~150 KB) resident in shared memory for all T steps.
+//   S = 1  clusters of 4: CTA rank = gate, M = 64 tiles, K = H          (small H; the round-1 shape)
+//   S = 2  clusters of 8: CTA rank = 2*gate + K half, M = 128 tiles, K = H/2: half the MMA instructions per
+//          step (their cost does not depend on M), half the operand image to fetch
+// The partial products D_r[UC x B] are exchanged as a reduce-scatter by PUSHING: while draining TMEM, each
+// accumulator row is written straight from registers into the shared memory of the CTA that owns the row's
+// unit (st.async, the bytes are counted on the owner's mbarrier: no fence, no staging pass), and the owner adds
+// the partials in fixed order in its cell math.  (Round 1 staged them locally, announced them with a
+// cluster-scope release arrive -- a second MEMBAR.ALL.GPU per step -- and pulled them through DSMEM: 17 % slower,
+// still selectable for S = 1 with ZRB_BWD_PULL=1.)  dc lives in registers for the whole window; the bias
+// gradients sum_{t,b} dG are accumulated in registers and reduced over the batch at the end of the kernel.
 //
-// Per step and CTA: one 72 KB bulk copy (gate r's dG image), H/16 tcgen05.mma (M=64, N=pad8(B), K=16),
-// a 4-way DSMEM reduction of U*B floats, U*B cell updates, one grid-barrier arrival.
-// Roofline: latency / shared-memory bound like the forward kernel; flops per layer call 8*T*B*H^2.
+// Per step and CTA: a bulk copy of its part of its gate's dG image (47-72 KB, four pieces), H/(16*S)
+// tcgen05.mma, the push exchange, U*B cell updates, one grid-barrier arrival.
+// Roofline: latency / L2 bound like the forward kernel; flops per layer call 8*T*B*H^2.
 #include <stdlib.h>
 
 #include "rec_common.cuh"

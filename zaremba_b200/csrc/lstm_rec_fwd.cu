@@ -2,10 +2,13 @@
 //
 //   for t in 0..T-1:   gates_t = XG_t + h_{t-1} * W_hh^T ;  (i,f,g,o) ;  c_t, h_t     (model.py:34-45)
 //
-// Work split: CTA k owns U hidden units j in [k*U, k*U+U) and the 4U gate rows that produce
-// them.  Its slice of W_hh (fp16, 4U x H) is loaded ONCE into shared memory in the canonical
-// no-swizzle K-major UMMA layout and stays there for all T steps (weight-stationary); c_t lives in
-// registers of the epilogue threads for the whole window.
+// Work split: CTA k owns U hidden units j in [k*U, k*U+U) (their cell math, c_t in registers for the whole
+// window).  The slice of W_hh a CTA multiplies with (fp16, ~144 KB) is loaded ONCE into shared memory in the
+// canonical no-swizzle K-major UMMA layout and stays there for all T steps (weight-stationary):
+//   SPLIT = false  the 4U gate rows of its own units x the whole contraction, M = 64 tiles   (H < 256)
+//   SPLIT = true   CTA PAIRS (clusters of 2): the 8U gate rows of the pair's units x ONE HALF of the contraction,
+//                  M = 128 tiles; see the note above RecFwdArgs.  The description below is the SPLIT = false flow;
+//                  with SPLIT the drain pushes rows to their owner instead of staging them.
 //
 // Per step:
 //   loader thread   polls the grid-barrier counter (relaxed loads, one fence.acquire.gpu after the last
