@@ -423,6 +423,8 @@ static TileChoice choose_tiles(int M, int N, int num_kb, bool can_split) {
         return c;
     }
     c.bn = (t256 >= (nsm * 9) / 10) ? 256 : 128;
+    static const int force_bn = [] { const char* e = getenv("ZRB_GEMM_BN"); return e ? atoi(e) : 0; }();   // experiment switch
+    if (force_bn == 128 || force_bn == 256) c.bn = force_bn;
     c.tiles_n = cdiv(N, c.bn);
     // few output tiles but a long contraction: split K in two so that ~all SMs work; partials added into a
     // zeroed C with atomics
