@@ -60,6 +60,9 @@ struct GemmArgs {
                       // (the wgrads feed clip_grad_norm_ from here instead of re-reading 200 MB of gradients)
     float* C2;        // dual launch (or null): a second problem with the same A, shapes and pitches but its own B (tma_b2),
     float* sumsq_out2;  // output and sum-of-squares slots; work items [num_tiles, 2*num_tiles) belong to it (splits == 1)
+    const __half* a_tiled;   // EXPERIMENT (zrb_gemm_f16_tiled): pre-tiled, pre-swizzled K-major images ([K block][128-row
+    const __half* b_tiled;   // tile][128][64] halves, chunk c of row r stored at c ^ (r % 8)): operand tiles are fetched with
+    int a_nt128, b_nt128;    // 1-D bulk copies instead of 2-D tensor loads
     int pdl_tail;     // launched as a programmatic dependent of the kernel before it in the stream (it started while that
                       // kernel was still running and consumes none of its outputs): wait for that kernel before exiting,
                       // so that "this grid completed" keeps implying "everything before it in the stream completed"
@@ -124,14 +127,19 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 uint8_t* a = sA + s * kABytes;
                 uint8_t* b = sB + s * kBBytes;
                 for (int mt = 0; mt < mt_n; ++mt) {
-                    if (!A_MN) {
+                    if (!A_MN && p.a_tiled) {
+                        bulk_load_1d(a + mt * kASubBytes, p.a_tiled + ((size_t)kb * p.a_nt128 + ((m0 + mt * GBM) >> 7)) * (128 * GBK),
+                                     kASubBytes, &full[s]);
+                    } else if (!A_MN) {
                         tma_load_2d(a + mt * kASubBytes, &tma_a, &full[s], kb * GBK, m0 + mt * GBM);
                     } else {
                         tma_load_2d(a + mt * kASubBytes, &tma_a, &full[s], m0 + mt * GBM, kb * GBK);
                         tma_load_2d(a + mt * kASubBytes + kASubBytes / 2, &tma_a, &full[s], m0 + mt * GBM + 64, kb * GBK);
                     }
                 }
-                if (!B_MN) {
+                if (!B_MN && p.b_tiled) {
+                    bulk_load_1d(b, p.b_tiled + ((size_t)kb * p.b_nt128 + (n0 >> 7)) * (128 * GBK), kBBytes, &full[s]);
+                } else if (!B_MN) {
                     tma_load_2d(b, tmb, &full[s], kb * GBK, n0);
                 } else {
 #pragma unroll
@@ -440,7 +448,8 @@ int gemm_f16_tc_sumsq_slots(int M, int N, int K) {
 
 int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t ldb, int b_mn, float* C, int64_t ldc,
                 int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, float* sumsq_out,
-                const float* bias2, bool pdl, const __half* B2, float* C2, float* sumsq_out2) {
+                const float* bias2, bool pdl, const __half* B2, float* C2, float* sumsq_out2, const __half* A_tiled,
+                int a_nt128, const __half* B_tiled, int b_nt128) {
     if (M <= 0 || N <= 0) return ZRB_OK;
     ZRB_REQUIRE(!B2 == !C2, "dual launch needs both B2 and C2");
     ZRB_REQUIRE(!bias2 || bias, "bias2 needs bias");
@@ -465,6 +474,7 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
     a.sumsq_out = sumsq_out;
     a.bias2 = bias2;
     a.C2 = C2; a.sumsq_out2 = sumsq_out2;
+    a.a_tiled = a_mn ? nullptr : A_tiled; a.a_nt128 = a_nt128; a.b_tiled = b_mn ? nullptr : B_tiled; a.b_nt128 = b_nt128;
     a.pdl_tail = (pdl && a.splits == 1) ? 1 : 0;    // (a split launch is preceded by a memset: nothing to chain to)
     // split partials are added into a zeroed C: order-independent for two (a+b == b+a), last-bit run-to-run
     // differences beyond that
@@ -476,10 +486,21 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
 
 }  // namespace zrb
 
+// EXPERIMENT: the same GEMM (K-major A and B) with both operands given as pre-tiled images as well; a_nt128 / b_nt128 =
+// 128-row tiles per K block in the images (b_nt128 even)
+extern "C" int zrb_gemm_f16_tiled(const void* A, int64_t lda, const void* B, int64_t ldb, const void* A_tiled, int32_t a_nt128,
+                                  const void* B_tiled, int32_t b_nt128, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                                  float alpha, void* stream) {
+    ZRB_REQUIRE(A && B && C, "null argument");
+    return zrb::gemm_f16_tc((const __half*)A, lda, 0, (const __half*)B, ldb, 0, C, ldc, M, N, K, alpha, nullptr, 0,
+                            (cudaStream_t)stream, nullptr, nullptr, false, nullptr, nullptr, nullptr, (const __half*)A_tiled,
+                            a_nt128, (const __half*)B_tiled, b_nt128);
+}
+
 extern "C" int zrb_gemm_f16(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
                             int32_t b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, float alpha,
                             const float* bias, int32_t accumulate, void* stream) {
     ZRB_REQUIRE(A && B && C, "null argument");
     return zrb::gemm_f16_tc((const __half*)A, lda, a_mn_major, (const __half*)B, ldb, b_mn_major, C, ldc, M, N, K,
-                            alpha, bias, accumulate, (cudaStream_t)stream, nullptr, nullptr, false, nullptr, nullptr, nullptr);
+                            alpha, bias, accumulate, (cudaStream_t)stream, nullptr, nullptr, false, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0);
 }

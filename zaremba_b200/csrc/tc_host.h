@@ -13,7 +13,8 @@ int tc_make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
 int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t ldb, int b_mn, float* C, int64_t ldc,
                 int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s,
                 float* sumsq_out = nullptr, const float* bias2 = nullptr, bool pdl = false, const __half* B2 = nullptr,
-                float* C2 = nullptr, float* sumsq_out2 = nullptr);
+                float* C2 = nullptr, float* sumsq_out2 = nullptr, const __half* A_tiled = nullptr, int a_nt128 = 0,
+                const __half* B_tiled = nullptr, int b_nt128 = 0);
 // B2 / C2 (/ sumsq_out2): a second problem C2 = alpha * op(A) * op(B2)^T with the same A, shapes and pitches, computed
 // by the same launch (the two weight gradients of a layer share dG as their A operand).
 // pdl: launch as a programmatic dependent of the kernel enqueued just before it on `s` (which must be one of the
