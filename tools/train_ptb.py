@@ -48,6 +48,8 @@ ap.add_argument("--factor_epoch", type=int, default=6)
 ap.add_argument("--factor", type=float, default=1.2)
 ap.add_argument("--max_grad_norm", type=float, default=5)
 ap.add_argument("--seed", type=int, default=0)
+ap.add_argument("--eval_batch_size", type=int, default=None,
+                help="batch size of the validation / test sweeps (default: --batch_size, like main.py)")
 ap.add_argument("--epochs", type=int, default=None, help="stop after this many epochs (schedule unchanged)")
 ap.add_argument("--json", default=None, help="write per-epoch validation perplexities, test perplexity, timing here")
 ap.add_argument("--save", default=None, help="save the trained state_dict (reference key names) here")
@@ -83,8 +85,9 @@ dev = torch.device("cuda", local)
 trn, vld, tst, vocab = data_init_text(args.data) if args.data else data_init_ids(args.ids)
 B, T = args.batch_size, args.seq_length
 trn_b = zaremba_b200.minibatch(parallel.shard_rows(trn, B, rank, world), B, T)
-vld_b = zaremba_b200.minibatch(vld, B, T)
-tst_b = zaremba_b200.minibatch(tst, B, T)
+EB = args.eval_batch_size or B
+vld_b = zaremba_b200.minibatch(vld, EB, T)
+tst_b = zaremba_b200.minibatch(tst, EB, T)
 torch.manual_seed(args.seed)
 
 if args.impl == "ours":
@@ -128,10 +131,10 @@ else:
     def perplexity(batches):                           # main.py:86-95
         model.eval()
         with torch.no_grad():
-            losses, states = [], model.zero_state(B)
+            losses, states = [], model.zero_state(EB)
             for x, y in batches:
                 logits, states = model(x.to(dev), states)
-                losses.append(P.softmax_nll_times_batch(logits, y.to(dev)).item() / B)
+                losses.append(P.softmax_nll_times_batch(logits, y.to(dev)).item() / EB)
         return float(np.exp(np.mean(losses)))
 
     def state_dict():
