@@ -48,6 +48,8 @@ ap.add_argument("--factor_epoch", type=int, default=6)
 ap.add_argument("--factor", type=float, default=1.2)
 ap.add_argument("--max_grad_norm", type=float, default=5)
 ap.add_argument("--seed", type=int, default=0)
+ap.add_argument("--lazy_update", action="store_true",
+                help="Trainer(lazy_update=True): upper-layer / fc weight updates run beside the next step's forward")
 ap.add_argument("--eval_batch_size", type=int, default=None,
                 help="batch size of the validation / test sweeps (default: --batch_size, like main.py)")
 ap.add_argument("--epochs", type=int, default=None, help="stop after this many epochs (schedule unchanged)")
@@ -92,7 +94,7 @@ torch.manual_seed(args.seed)
 
 if args.impl == "ours":
     model = zaremba_b200.Model(vocab, args.hidden_size, args.layer_num, args.dropout, args.winit).to(dev)
-    tr = zaremba_b200.Trainer(model, B, T)
+    tr = zaremba_b200.Trainer(model, B, T, lazy_update=args.lazy_update)
     # the corpus is staged on the device once: 3 x [n_batches, T, B] int64
     trn_x = torch.stack([x for x, _ in trn_b]).contiguous().to(dev)
     trn_y = torch.stack([y for _, y in trn_b]).contiguous().to(dev)
@@ -111,6 +113,7 @@ if args.impl == "ours":
         return tr.perplexity(batches)
 
     def state_dict():
+        tr.flush()
         return {k: v.detach().cpu() for k, v in model.state_dict().items()}
 else:
     if world > 1:
