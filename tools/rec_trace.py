@@ -27,5 +27,9 @@ for d, nm in enumerate(["fwd", "bwd"]):
     x = a[d][2:T - 1]                       # steady-state steps
     step = np.diff(a[d][1:, 0]).mean()
     rel = (x - x[:, :1]).mean(0)
-    out[nm] = {"clk_per_step": float(step), "phase_offsets_clk": dict(zip(names, [float(v) for v in rel]))}
+    out[nm] = {"clk_per_step": float(step), "phase_offsets_clk": dict(zip(names, [float(v) for v in rel])),
+               # the launch's first steps: step 0 has no barrier to wait for but starts with the weight-slice load
+               "step_starts_clk_rel_to_step0": [int(v - a[d][0, 0]) for v in a[d][:5, 0]],
+               "step0_phase_offsets_clk": dict(zip(names, [int(v - a[d][0, 0]) for v in a[d][0]])),
+               "whole_window_clk": int(a[d][T - 1, 7] - a[d][0, 0])}
 print(json.dumps(out, indent=1))
