@@ -256,8 +256,9 @@ int  zrb_prof_enable(zrb_ctx* ctx, int32_t on);
 int  zrb_prof_read(zrb_ctx* ctx, float* h_ms, int64_t* h_counts);
 /* Phase timeline of the persistent recurrence kernels (clock64 stamps of CTA 0, 8 per step:
  * barrier seen, operand landed, MMAs issued, accumulator ready, TMEM drained, cell math start/end,
- * arrival).  Needs ZRB_REC_TRACE=1 in the environment at context creation.  Returns the number of
- * entries written ([fwd|bwd][T][8]) or a negative error. */
+ * arrival), preceded per kernel by 8 launch slots: CTA 0's clock64 at kernel entry / exit, its %globaltimer (ns)
+ * at entry / exit, -(earliest CTA entry ns), latest CTA exit ns, 2 spare.  Needs ZRB_REC_TRACE=1 in the environment
+ * at context creation.  Returns the number of entries written ([fwd|bwd][8 + T*8]) or a negative error. */
 int  zrb_prof_rec_trace(zrb_ctx* ctx, int64_t* h_out, int32_t max_entries);
 
 /* ---- building blocks, exported for unit tests and profiling ------------------------ */

@@ -215,6 +215,45 @@ def test_lazy_update_equals_strict_update():
     torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-6, atol=1e-7)
 
 
+def test_recurrence_launch_modes_agree():
+    """The persistent recurrence kernels are launched as programmatic dependents of the GEMM before them while ONE
+    tcgen05 context is alive on the device, and cooperatively as soon as a second one exists (tc_common.cuh,
+    rec_launch_programmatic): both launches must give the same bits.  H = 256 takes the K-split (cluster) kernels."""
+    import gc
+    import zaremba_b200
+    V, H, L, T, B = 500, 256, 2, 9, 8
+    g = torch.Generator().manual_seed(11)
+    d = torch.randint(0, V, (B, 3 * T + 1), generator=g)
+
+    def run(tr):
+        out = []
+        for i in range(3):
+            x = d[:, i * T:(i + 1) * T].t().contiguous().to(_dev())
+            y = d[:, i * T + 1:(i + 1) * T + 1].t().contiguous().to(_dev())
+            loss, norm = tr.train_step(x, y, 1.0, 0.25)
+            out.append((loss.item(), norm.item()))
+        tr.flush()
+        torch.cuda.synchronize()
+        return out, tr.flat_p.clone()
+
+    def make():
+        torch.manual_seed(5)
+        m = zaremba_b200.Model(V, H, L, 0.0, 0.1).to(_dev())
+        m.train()
+        return m, zaremba_b200.Trainer(m, B, T)
+
+    gc.collect()
+    m1, t1 = make()
+    alone = run(t1)                 # (programmatic if no context of an earlier test is still alive)
+    t1.close(); del m1, t1
+    gc.collect()
+    m2, t2 = make()
+    m3, t3 = make()                 # a second live context: both now launch cooperatively
+    both = run(t2)
+    assert alone[0] == both[0], (alone[0], both[0])
+    assert torch.equal(alone[1], both[1])
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_host_buffer_step_equals_device_step(engine):
     """zrb_train_step_host (H2D/D2H inside) == device-token step, bit for bit in eval of loss."""

@@ -12,6 +12,7 @@ namespace zrb {
 
 static thread_local char t_err[1024] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_live_tc_ctx[64];
 
 void set_error(const char* fmt, ...) {
     va_list ap;

@@ -12,6 +12,7 @@ namespace zrb {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int> g_live_tc_ctx[64];   // live tcgen05-engine contexts per device (index = device & 63)
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 #define ZRB_CUDA(call)                                                                   \

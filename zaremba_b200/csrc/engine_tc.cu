@@ -16,6 +16,7 @@
 
 struct zrb_tc_state {
     int Hp = 0, G4p = 0, Vp = 0;
+    int device = 0;
     __half* w_ih_h[ZRB_MAX_LAYERS] = {};
     __half* w_hh_h[ZRB_MAX_LAYERS] = {};
     __half* fc_w_h = nullptr;
@@ -49,7 +50,7 @@ struct zrb_tc_state {
     zrb::RecPlan bplan{};
     __half* w_img_b[ZRB_MAX_LAYERS] = {};
     __half* g_img = nullptr;
-    long long* trace = nullptr;   // [2][T][8] clock stamps (zrb_prof_rec_trace)
+    long long* trace = nullptr;   // [2][8 + T*8]: launch stamps + per-step clock stamps (zrb_prof_rec_trace)
     // fused step (zrb_set_embed_sparse): the wgrad GEMMs leave sums of squares of the matrix gradients in
     // c->partials, so clip_grad_norm_ does not re-read them; valid for the gradient buffers keyed by wg_key
     bool wg_ok = false;
@@ -88,6 +89,8 @@ int tc_ctx_init(zrb_ctx* c) {
     }
     c->tc = new zrb_tc_state();
     zrb_tc_state* t = c->tc;
+    t->device = dev & 63;
+    g_live_tc_ctx[t->device].fetch_add(1);
     const int H = c->cfg.hidden, L = c->cfg.layers, V = c->cfg.vocab;
     const size_t N = (size_t)c->cfg.max_seq * c->cfg.max_batch, B = c->cfg.max_batch;
     t->Hp = pad64(H); t->G4p = pad64(4 * H); t->Vp = pad64(V);
@@ -114,7 +117,7 @@ int tc_ctx_init(zrb_ctx* c) {
         ZRB_TRY(tc_alloc(c, &t->h_img, (size_t)(c->cfg.max_seq + 1) * fp.Kc * fp.GBi * 64));
         ZRB_TRY(tc_alloc(c, &t->counter, 64));
     }
-    if (getenv("ZRB_REC_TRACE")) ZRB_TRY(tc_alloc(c, &t->trace, (size_t)2 * c->cfg.max_seq * 8));
+    if (getenv("ZRB_REC_TRACE")) ZRB_TRY(tc_alloc(c, &t->trace, (size_t)2 * (8 + c->cfg.max_seq * 8)));
     ZRB_TRY(rec_bwd_plan(H, c->cfg.max_batch, &t->bplan));
     if (!t->fplan.ok || (force && !strcmp(force, "fwdonly"))) t->bplan.ok = 0;
     if (t->bplan.ok) {
@@ -127,6 +130,7 @@ int tc_ctx_init(zrb_ctx* c) {
 
 void tc_ctx_free(zrb_ctx* c) {
     if (!c->tc) return;
+    g_live_tc_ctx[c->tc->device].fetch_sub(1);
     for (void* p : c->tc->allocs) cudaFree(p);
     delete c->tc;
     c->tc = nullptr;
@@ -351,7 +355,7 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
             }
             ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], dG_h,
                                  t->counter + 32, t->cnt_b, T, B, H, G4p, m, s,
-                                 t->trace ? t->trace + (size_t)c->cfg.max_seq * 8 : nullptr, g->b_ih[l], g->b_hh[l],
+                                 t->trace ? t->trace + 8 + (size_t)c->cfg.max_seq * 8 : nullptr, g->b_ih[l], g->b_hh[l],
                                  c->resident_flag, ++c->resident_seq, c->dG /* [N,4H] fp32, idle on this path */));
             t->cnt_b += arrivals;
             ZRB_TRY(tc_issue_pending(c, g, s));   // runs on the SMs the cluster kernel leaves idle
@@ -529,7 +533,7 @@ int tc_layer_bwd(zrb_ctx* c, const float* dy, float* dx, float* dw_ih, float* dw
 
 int tc_rec_trace(zrb_ctx* c, long long* h_out, int max_entries) {
     if (!c->tc || !c->tc->trace) { set_error("set ZRB_REC_TRACE=1 before creating the context"); return ZRB_E_STATE; }
-    int n = 2 * c->cfg.max_seq * 8;
+    int n = 2 * (8 + c->cfg.max_seq * 8);
     if (n > max_entries) n = max_entries;
     ZRB_CUDA(cudaDeviceSynchronize());
     ZRB_CUDA(cudaMemcpy(h_out, c->tc->trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));

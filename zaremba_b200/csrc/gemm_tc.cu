@@ -63,6 +63,7 @@ struct GemmArgs {
     const __half* a_tiled;   // EXPERIMENT (zrb_gemm_f16_tiled): pre-tiled, pre-swizzled K-major images ([K block][128-row
     const __half* b_tiled;   // tile][128][64] halves, chunk c of row r stored at c ^ (r % 8)): operand tiles are fetched with
     int a_nt128, b_nt128;    // 1-D bulk copies instead of 2-D tensor loads
+    int pdl_trigger;  // release a programmatic dependent enqueued behind this kernel (a recurrence kernel) at once
     int pdl_tail;     // launched as a programmatic dependent of the kernel before it in the stream (it started while that
                       // kernel was still running and consumes none of its outputs): wait for that kernel before exiting,
                       // so that "this grid completed" keeps implying "everything before it in the stream completed"
@@ -99,6 +100,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const int kb_per = (num_kb + p.splits - 1) / p.splits;              //   K range (split-K) or problem (dual launch)
 
     if (threadIdx.x == 0) {
+        if (p.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (dual) tma_prefetch_desc(&tma_b2);
@@ -476,6 +478,7 @@ int gemm_f16_tc(const __half* A, int64_t lda, int a_mn, const __half* B, int64_t
     a.C2 = C2; a.sumsq_out2 = sumsq_out2;
     a.a_tiled = a_mn ? nullptr : A_tiled; a.a_nt128 = a_nt128; a.b_tiled = b_mn ? nullptr : B_tiled; a.b_nt128 = b_nt128;
     a.pdl_tail = (pdl && a.splits == 1) ? 1 : 0;    // (a split launch is preceded by a memset: nothing to chain to)
+    a.pdl_trigger = (rec_pdl_enabled() && !a.pdl_tail) ? 1 : 0;
     // split partials are added into a zeroed C: order-independent for two (a+b == b+a), last-bit run-to-run
     // differences beyond that
     if (a.splits > 1 && !accumulate) ZRB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s));

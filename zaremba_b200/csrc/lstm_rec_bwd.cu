@@ -46,7 +46,7 @@ struct RecBwdArgs {
     int T, B, H, G4p, U, G, GB, Kc, nCTA;
     int KcS, GBi;             // K chunks per CTA (Kc / S); 8-row batch groups of the dG images (GB, or 4 when N = 32)
     MaskSrc m;
-    long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
+    long long* trace;         // optional (profiling): [8] launch stamps (rec_launch_stamps) + [T][8] clock64 stamps of CTA 0
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     const int ksteps = a.KcS / 2;
     const int piece_steps = (ksteps + kRecPieces - 1) / kRecPieces;
     const bool tr = a.trace != nullptr && blockIdx.x == 0;
+    long long* const trs = a.trace + 8;
+    if (a.trace && threadIdx.x == 0) rec_launch_stamps(a.trace, tr, false);
 
     if (threadIdx.x == 0) {
         mbar_init(bar_a, 1);
@@ -148,13 +150,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     cluster_sync_all();   // every CTA's mbarriers are initialised before any remote arrive
-    if (threadIdx.x == 0) pdl_launch_dependents();
 
     if (warp == kRecLoadWarp && lane == 0) {
         // ===================== loader =====================
         const uint8_t* src = (const uint8_t*)a.w_img + ((size_t)cluster * CS + rank) * a_bytes;
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
+        pdl_wait();   // everything below reads what the preceding kernel wrote
         const int lbo_b = a.GBi * 128;
         const size_t gate_bytes = (size_t)a.Kc * a.GBi * 128;   // one gate's whole dG image
         const bool publish = a.res_flag != nullptr && blockIdx.x == 0;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             grid_counter_wait(a.counter, a.base + (unsigned int)s * a.nCTA);
             if (publish && s == 1)   // every CTA arrived once: the whole grid is resident
                 asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.res_flag), "r"(a.res_value) : "memory");
-            if (tr) a.trace[s * 8 + 0] = clock64();
+            if (tr) trs[s * 8 + 0] = clock64();
             fence_proxy_async_global();
             const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + gate) * gate_bytes +
                                  (size_t)khalf * b_bytes;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             for (int pc = 0; pc < kRecPieces; ++pc) {
                 bounded_mbar_wait(&bar_b[pc], (s - 1) & 1);
                 tcgen05_fence_after();
-                if (tr && pc == 0 && me == 0) a.trace[s * 8 + 1] = clock64();
+                if (tr && pc == 0 && me == 0) trs[s * 8 + 1] = clock64();
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
                 for (int ks = k0 + ((me - k0) & (kRecMmaWarps - 1)); ks < k1; ks += kRecMmaWarps) {
                     uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
@@ -197,9 +199,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 }
             }
             umma_commit(bar_mma);
-            if (tr && me == 0) a.trace[s * 8 + 2] = clock64();
+            if (tr && me == 0) trs[s * 8 + 2] = clock64();
         }
     } else if (warp < kRecEpiWarps) {
+        pdl_wait();
+        if (threadIdx.x == 0) pdl_launch_dependents();   // after the wait: dependents of this kernel keep stream order with its predecessor
         // ===================== epilogue: 256 threads, cells (u, b) of this CTA's U units =====================
         const int tid = threadIdx.x;
         const int cells = a.U * B;                     // cell = b * U + u (u fastest: contiguous j)
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 if (push && tid == 0) mbar_expect_tx(bar_recv, recv_bytes);
                 bounded_mbar_wait(bar_mma, (s - 1) & 1);
                 tcgen05_fence_after();
-                if (tr && tid == 0) a.trace[s * 8 + 3] = clock64();
+                if (tr && tid == 0) trs[s * 8 + 3] = clock64();
                 // TMEM -> own shared staging: accumulator row i (cluster-local unit) in lane (i%16)+32*(i/16)
                 {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
                     // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 tcgen05_fence_before();
                 if (!push) {
                     asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
+                    if (tr && tid == 0) trs[s * 8 + 4] = clock64();
                     if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
                     {   // wait until all four CTAs of the cluster staged their partials
                         uint32_t n = 0; long long t0 = 0;
@@ -305,11 +309,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                         }
                     }
                 } else {
-                    if (tr && tid == 0) a.trace[s * 8 + 4] = clock64();
+                    if (tr && tid == 0) trs[s * 8 + 4] = clock64();
                     bounded_mbar_wait(bar_recv, (s - 1) & 1);   // all CS x U x Bp partial sums of my units have landed
                 }
             }
-            if (tr && tid == 0) a.trace[s * 8 + 5] = clock64();
+            if (tr && tid == 0) trs[s * 8 + 5] = clock64();
             __half hv[kRecMaxCell][4];
 #pragma unroll
             for (int k = 0; k < kRecMaxCell; ++k) {
@@ -354,11 +358,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     bsum[k][q] += dg4[q];
                 }
             }
-            if (tr && tid == 0) a.trace[s * 8 + 6] = clock64();
+            if (tr && tid == 0) trs[s * 8 + 6] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
                 grid_counter_arrive(a.counter);
-                if (tr) a.trace[s * 8 + 7] = clock64();
+                if (tr) trs[s * 8 + 7] = clock64();
             }
             // off the critical path: row-major image for the batched dgrad / wgrad GEMMs
 #pragma unroll
@@ -403,6 +407,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
     tcgen05_fence_after();
     if (warp == kRecMmaWarp) tmem_dealloc<kRecTmemCols>(tmem_d);
     cluster_sync_all();   // no CTA leaves while a peer may still read its staged partial
+    if (a.trace && threadIdx.x == 0) rec_launch_stamps(a.trace, tr, true);
 }
 
 // w_img[cluster][rank][kcl][g][rr][e] = half(W_hh[gate*H + (khalf*KcS + kcl)*8 + e, cluster*UC + g*8 + rr]) with
@@ -537,14 +542,17 @@ static int launch_rec_bwd(const RecPlan& p, const RecBwdArgs& a, cudaStream_t s)
     cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-    attrs[1].id = cudaLaunchAttributeCooperative;
-    attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
-    // The grid barrier needs all nCTA CTAs co-resident.  The cooperative attribute makes the driver guarantee it (or
-    // refuse the launch); see rec_bwd_no_coop() for the profiler case.
-    const bool no_coop = rec_bwd_no_coop();
+    // The grid barrier needs all nCTA CTAs co-resident.  Either the cooperative attribute makes the driver guarantee it
+    // (or refuse the launch), or -- one context on the device, or under a profiler (rec_bwd_no_coop()) -- a plain cluster
+    // launch checked against the occupancy query, with the programmatic attribute so that the CTAs start behind the
+    // preceding GEMM's trigger (tc_common.cuh, rec_launch_programmatic()).
+    const bool programmatic = rec_launch_programmatic(dev) && !a.trace;
+    const bool no_coop = programmatic || rec_bwd_no_coop();
     cudaError_t e = cudaSuccess;
     if (!no_coop) {
+        attrs[1].id = cudaLaunchAttributeCooperative;
+        attrs[1].val.cooperative = 1;
         cfg.numAttrs = 2;
         e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel<S>, a);
         if (e == cudaErrorCooperativeLaunchTooLarge) {
@@ -557,13 +565,21 @@ static int launch_rec_bwd(const RecPlan& p, const RecBwdArgs& a, cudaStream_t s)
     }
     if (no_coop || e != cudaSuccess) {
         cfg.numAttrs = 1;
-        int max_clusters = 0;
-        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_bwd_kernel<S>, &cfg);
-        if (oe != cudaSuccess || max_clusters * CS < p.nCTA) {
-            (void)cudaGetLastError();
-            set_error("lstm_rec_bwd: %d clusters of %d needed, the device can hold %d at once (%s)", p.nCTA / CS, CS,
-                      max_clusters, oe == cudaSuccess ? "grid would not be co-resident" : cudaGetErrorString(oe));
+        static int seen_dev = -1, seen_smem = -1, seen_max = 0;   // the query is a host call: once per (device, footprint)
+        if (seen_dev != dev || seen_smem != p.smem) {
+            int max_clusters = 0;
+            cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_bwd_kernel<S>, &cfg);
+            if (oe != cudaSuccess) { (void)cudaGetLastError(); max_clusters = 0; }
+            seen_dev = dev; seen_smem = p.smem; seen_max = max_clusters;
+        }
+        if (seen_max * CS < p.nCTA) {
+            set_error("lstm_rec_bwd: %d clusters of %d needed, the device can hold %d at once", p.nCTA / CS, CS, seen_max);
             return ZRB_E_CUDA;
+        }
+        if (programmatic) {
+            attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.numAttrs = 2;
         }
         e = cudaLaunchKernelEx(&cfg, lstm_rec_bwd_kernel<S>, a);
     }
@@ -588,6 +604,7 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     a.counter = counter; a.db1 = db1; a.db2 = db2; a.db_scratch = db_scratch; a.res_flag = resident_flag; a.res_value = resident_value;
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     a.KcS = p.KcS; a.GBi = p.GBi;
+    if (trace) ZRB_CUDA(cudaMemsetAsync(trace + 4, 0x80, 2 * sizeof(long long), s));
     return p.KS == 2 ? launch_rec_bwd<2>(p, a, s) : launch_rec_bwd<1>(p, a, s);
 }
 

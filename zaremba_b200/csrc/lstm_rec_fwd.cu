@@ -62,7 +62,7 @@ struct RecFwdArgs {
     int T, B, H, Hp, U, G, GB, Kc, nCTA;
     int KcS, GBi;             // K chunks per CTA (Kc / KS); 8-row batch groups of the operand image (GB, or 4 when N = 32)
     MaskSrc m;
-    long long* trace;         // optional [T][8] clock64 stamps of CTA 0 (profiling)
+    long long* trace;         // optional (profiling): [8] launch stamps (rec_launch_stamps) + [T][8] clock64 stamps of CTA 0
 };
 
 __device__ __forceinline__ uint32_t fwd_cluster_ctarank() {
@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     const int ksteps = a.KcS / 2;
     const int piece_steps = (ksteps + kRecPieces - 1) / kRecPieces;
     const bool tr = a.trace != nullptr && cta == 0;
+    long long* const trs = a.trace + 8;
+    if (a.trace && threadIdx.x == 0) rec_launch_stamps(a.trace, tr, false);
 
     if (threadIdx.x == 0) {
         mbar_init(bar_a, 1);
@@ -126,18 +128,18 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     if (SPLIT) fwd_cluster_sync();   // the partner's mbarriers are initialised before any st.async targets them
-    if (threadIdx.x == 0) pdl_launch_dependents();
 
     if (warp == kRecLoadWarp && lane == 0) {
         // ===================== loader =====================
         const uint8_t* src = (const uint8_t*)a.w_img + (size_t)cta * a_bytes;
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
+        pdl_wait();   // everything below reads what the preceding kernel wrote
         const int lbo_b = a.GBi * 128;
         const size_t img_bytes = (size_t)a.Kc * a.GBi * 128;   // one whole h image; this CTA reads K chunks [rank*KcS, +KcS)
         for (int t = 0; t < a.T; ++t) {
             if (t > 0) grid_counter_wait(a.counter, a.base + (unsigned int)t * a.nCTA);
-            if (tr) a.trace[t * 8 + 0] = clock64();
+            if (tr) trs[t * 8 + 0] = clock64();
             fence_proxy_async_global();
             const uint8_t* img = (t == 0 ? (const uint8_t*)a.h0_img : (const uint8_t*)a.h_img + (size_t)t * img_bytes) +
                                  (size_t)rank * b_bytes;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             for (int pc = 0; pc < kRecPieces; ++pc) {
                 bounded_mbar_wait(&bar_b[pc], t & 1);
                 tcgen05_fence_after();
-                if (tr && pc == 0 && me == 0) a.trace[t * 8 + 1] = clock64();
+                if (tr && pc == 0 && me == 0) trs[t * 8 + 1] = clock64();
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
                 for (int ks = k0 + ((me - k0) & (kRecMmaWarps - 1)); ks < k1; ks += kRecMmaWarps) {
                     uint64_t da = make_smem_desc(a_addr + ks * 2 * lbo_a, lbo_a, 128, kSwizzleNone);
@@ -170,9 +172,11 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 }
             }
             umma_commit(bar_mma);
-            if (tr && me == 0) a.trace[t * 8 + 2] = clock64();
+            if (tr && me == 0) trs[t * 8 + 2] = clock64();
         }
     } else if (warp < kRecEpiWarps) {
+        pdl_wait();
+        if (threadIdx.x == 0) pdl_launch_dependents();   // after the wait: dependents of this kernel keep stream order with its predecessor
         // ===================== epilogue: 256 threads =====================
         const int tid = threadIdx.x;
         const int B = a.B, H = a.H;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             }
             bounded_mbar_wait(bar_mma, t & 1);
             tcgen05_fence_after();
-            if (tr && tid == 0) a.trace[t * 8 + 3] = clock64();
+            if (tr && tid == 0) trs[t * 8 + 3] = clock64();
             {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
                 // (an issuer with no K step leaves its accumulator unwritten: skipped by a warp-uniform test).
                 // Accumulator row i sits in lane (i % 16) + 32 * (i / 16).
@@ -251,9 +255,9 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             tcgen05_fence_before();
             if (!SPLIT) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (tr && tid == 0) a.trace[t * 8 + 4] = clock64();
+                if (tr && tid == 0) trs[t * 8 + 4] = clock64();
             } else {
-                if (tr && tid == 0) a.trace[t * 8 + 4] = clock64();
+                if (tr && tid == 0) trs[t * 8 + 4] = clock64();
                 bounded_mbar_wait(bar_recv, t & 1);   // both K halves of my 4U rows have landed
             }
             float o_i[kRecMaxCell], o_f[kRecMaxCell], o_g[kRecMaxCell], o_o[kRecMaxCell], o_h[kRecMaxCell];
@@ -290,12 +294,12 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 __half* img = a.h_img + (size_t)(t + 1) * ((size_t)a.Kc * a.GBi * 64);
                 img[((size_t)(j >> 3) * a.GBi + (b >> 3)) * 64 + (b & 7) * 8 + (j & 7)] = __float2half_rn(h);
             }
-            if (tr && tid == 0) a.trace[t * 8 + 5] = clock64();
+            if (tr && tid == 0) trs[t * 8 + 5] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
-                if (tr) a.trace[t * 8 + 6] = clock64();
+                if (tr) trs[t * 8 + 6] = clock64();
                 grid_counter_arrive(a.counter);
-                if (tr) a.trace[t * 8 + 7] = clock64();
+                if (tr) trs[t * 8 + 7] = clock64();
             }
             // off the critical path: what backward and the next layer read after this kernel
 #pragma unroll
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
     tcgen05_fence_after();
     if (warp == kRecMmaWarp) tmem_dealloc<kRecTmemCols>(tmem_d);
     if (SPLIT) fwd_cluster_sync();   // nobody leaves while the partner could still address its shared memory
+    if (a.trace && threadIdx.x == 0) rec_launch_stamps(a.trace, tr, true);
 }
 
 // ---- weight / state image builders ---------------------------------------------------------------
@@ -434,6 +439,7 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
     a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
     a.KcS = p.KcS; a.GBi = p.GBi;
     a.trace = trace;
+    if (trace) ZRB_CUDA(cudaMemsetAsync(trace + 4, 0x80, 2 * sizeof(long long), s));
     if (p.KS == 1) {
         void* args[] = {&a};
         ZRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_rec_fwd_kernel<false>, dim3(p.nCTA), dim3(kRecThreads), args,
@@ -449,11 +455,14 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
     cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-    attrs[1].id = cudaLaunchAttributeCooperative;
-    attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
     cudaError_t e = cudaSuccess;
-    if (!rec_no_coop()) {
+    // cooperative, or plain + programmatic behind the input GEMM: tc_common.cuh, rec_launch_programmatic()
+    const bool programmatic = rec_launch_programmatic(dev) && !trace;
+    const bool plain = programmatic || rec_no_coop();
+    if (!plain) {
+        attrs[1].id = cudaLaunchAttributeCooperative;
+        attrs[1].val.cooperative = 1;
         cfg.numAttrs = 2;
         e = cudaLaunchKernelEx(&cfg, lstm_rec_fwd_kernel<true>, a);
         if (e == cudaErrorCooperativeLaunchTooLarge) {
@@ -463,14 +472,23 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
         }
         if (e != cudaSuccess) (void)cudaGetLastError();
     }
-    if (rec_no_coop() || e != cudaSuccess) {
+    if (plain || e != cudaSuccess) {
         cfg.numAttrs = 1;
-        int max_clusters = 0;
-        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_fwd_kernel<true>, &cfg);
-        if (oe != cudaSuccess || max_clusters * 2 < p.nCTA) {
-            (void)cudaGetLastError();
-            set_error("lstm_rec_fwd: %d CTA pairs needed, the device can hold %d at once", p.nCTA / 2, max_clusters);
+        static int seen_dev = -1, seen_smem = -1, seen_max = 0;   // the query is a host call: once per (device, footprint)
+        if (seen_dev != dev || seen_smem != p.smem) {
+            int max_clusters = 0;
+            cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec_fwd_kernel<true>, &cfg);
+            if (oe != cudaSuccess) { (void)cudaGetLastError(); max_clusters = 0; }
+            seen_dev = dev; seen_smem = p.smem; seen_max = max_clusters;
+        }
+        if (seen_max * 2 < p.nCTA) {
+            set_error("lstm_rec_fwd: %d CTA pairs needed, the device can hold %d at once", p.nCTA / 2, seen_max);
             return ZRB_E_CUDA;
+        }
+        if (programmatic) {
+            attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.numAttrs = 2;
         }
         e = cudaLaunchKernelEx(&cfg, lstm_rec_fwd_kernel<true>, a);
     }

@@ -50,6 +50,23 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 // resident), a kernel enqueued behind it with the programmatic-serialization attribute may start on the SMs this grid
 // leaves idle (148 - 125 / 128).  Kernels launched normally behind it are unaffected.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The other side: when THIS kernel was launched with the programmatic-serialization attribute behind a kernel that
+// triggers early (the tensor-core GEMMs do), its CTAs become resident -- mbarriers, TMEM, the resident weight slice on
+// its way -- while that kernel is still running; every thread that reads global memory the predecessor wrote calls this
+// first.  Returns at once in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Profiling only (ZRB_REC_TRACE): the 8 launch slots in front of the per-step stamps.  Called by thread 0 of EVERY CTA at
+// kernel entry (exit = false) and as its last instruction (exit = true):
+//   [0]/[1] CTA 0's clock64 at entry / exit      [2]/[3] CTA 0's %globaltimer (ns) at entry / exit
+//   [4] max over CTAs of -(entry %globaltimer)   [5] max over CTAs of the exit %globaltimer   (the host presets both
+//   to the most negative value before each launch) -> [5] + [4] = lifetime of the whole grid in ns
+__device__ __forceinline__ void rec_launch_stamps(long long* slots, bool cta0, bool exit) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    if (cta0) { slots[exit ? 1 : 0] = clock64(); slots[exit ? 3 : 2] = gt; }
+    atomicMax(slots + (exit ? 5 : 4), exit ? gt : -gt);
+}
 
 // sigmoid / tanh on the SFU exp path (abs error ~1e-7, far below the fp16 operand noise of this engine)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -8,7 +8,30 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+#include "common.cuh"
+
 namespace zrb {
+// host: how the persistent recurrence kernels are launched.
+//   cooperative  -- the driver guarantees that the whole grid is co-resident (the grid barrier needs it) or refuses;
+//   programmatic -- a plain cluster launch, checked against cudaOccupancyMaxActiveClusters, with the programmatic-
+//                   serialization attribute: the GEMM enqueued before it triggers at its start, so the recurrence CTAs
+//                   take SMs as the GEMM's CTAs retire and fetch their resident weight slices while its tail is still
+//                   running (pdl_wait in the kernels).  9 us per train step at the Large config; the cooperative
+//                   attribute suppresses the early start (measured: no gain with both attributes).
+// A plain launch is only as safe as the occupancy check: two persistent grids launched at the same time from two
+// streams could each get part of the device and spin on their barriers (until the bounded waits trap).  So the default
+// is programmatic only while ONE tcgen05 context is alive on the device -- a process that holds several (an ensemble,
+// two trainers) gets the cooperative launch.  ZRB_REC_PDL=0 forces cooperative, =1 forces programmatic.
+static inline int rec_pdl_env() {
+    static const int mode = [] { const char* e = getenv("ZRB_REC_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    return mode;
+}
+static inline bool rec_pdl_enabled() { return rec_pdl_env() != 0; }   // (GEMMs: trigger early; harmless before a cooperative launch)
+static inline bool rec_launch_programmatic(int dev) {
+    const int m = rec_pdl_env();
+    return m < 0 ? g_live_tc_ctx[dev & 63].load(std::memory_order_relaxed) <= 1 : m == 1;
+}
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
