@@ -184,6 +184,15 @@ int  zrb_set_keep_clipped_grads(zrb_ctx* ctx, int32_t on);
  * steps must be preceded by zrb_flush_updates(ctx, stream).  Same arithmetic, same order per element. */
 int  zrb_set_lazy_update(zrb_ctx* ctx, int32_t on);
 int  zrb_flush_updates(zrb_ctx* ctx, void* stream);
+
+/* Watchdog of the persistent recurrence kernels.  Every wait inside them is bounded (~3 s; ZRB_SPIN_CYCLES overrides).  A
+ * wait that runs out -- a lost wake-up, or a grid that never became co-resident -- does not trap: the kernel stops
+ * waiting everywhere, finishes with garbage in its outputs and leaves a code in a host-mapped word.  The next call on
+ * the context that launches or synchronises (zrb_forward / _eval_step / _train_step_* / _flush_updates; immediately for
+ * zrb_train_step_host, which synchronises itself) returns ZRB_E_CUDA with the wait, CTA and step in zrb_last_error();
+ * the zrb context stays failed, the CUDA context and the process are unharmed.  zrb_check_health reads that word
+ * (one host load, no synchronisation) -- for callers that keep everything on the device and want to poll. */
+int  zrb_check_health(zrb_ctx* ctx);
 int  zrb_embed_scatter_rows(zrb_ctx* ctx, float* grad_embed, const int64_t* ids, const float* rows,
                             int64_t n_rows, void* stream);
 int  zrb_train_step_update(zrb_ctx* ctx, const zrb_params* p, const zrb_params* grads,

@@ -38,7 +38,24 @@ static int dalloc(zrb_ctx* c, T** p, size_t count) {
     return dev_alloc(c, (void**)p, count * sizeof(T));
 }
 
+// A persistent recurrence kernel that ran out of patience (lost wake-up, grid not co-resident) finished with garbage and
+// left a code in the mapped host word: every later call on this context fails -- the CUDA context is intact, a new zrb
+// context works.  Costs one host load.
+static const char* const kWaitNames[] = {"?", "weight slice", "operand image", "accumulators", "partner rows", "grid barrier",
+                                         "cluster partials"};
+static int watchdog_check(const zrb_ctx* c) {
+    if (!c->wd_host) return ZRB_OK;
+    const unsigned int code = *(volatile const unsigned int*)c->wd_host;
+    if (code == 0) return ZRB_OK;
+    const unsigned int kind = code & 0xFF;
+    set_error("a persistent recurrence kernel gave up waiting for its %s (CTA %u, step %u): results since then are invalid and "
+              "this context is unusable; the CUDA context is intact",
+              kind < sizeof(kWaitNames) / sizeof(kWaitNames[0]) ? kWaitNames[kind] : "?", (code >> 8) & 0xFFF, code >> 20);
+    return ZRB_E_CUDA;
+}
+
 static int check_shapes(const zrb_ctx* c, int T, int B) {
+    ZRB_TRY(watchdog_check(c));
     ZRB_REQUIRE(T >= 1 && T <= c->cfg.max_seq, "T=%d outside [1,%d]", T, c->cfg.max_seq);
     ZRB_REQUIRE(B >= 1 && B <= c->cfg.max_batch, "B=%d outside [1,%d]", B, c->cfg.max_batch);
     return ZRB_OK;
@@ -119,6 +136,17 @@ int zrb_ctx_create(const zrb_config* cfg, zrb_ctx** out) {
     if (rc == ZRB_OK) c->emb_prev_cap = (int64_t)N;
     if (rc == ZRB_OK) rc = dalloc(c, &c->resident_flag, 4);
     if (rc == ZRB_OK && cudaMemset(c->resident_flag, 0, 4 * sizeof(unsigned int)) != cudaSuccess) rc = ZRB_E_CUDA;
+    if (rc == ZRB_OK) {
+        c->wd_flag = c->resident_flag + 2;
+        void* hp = nullptr;
+        if (cudaHostAlloc(&hp, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) {
+            set_error("cudaHostAlloc of the watchdog word failed");
+            rc = ZRB_E_CUDA;
+        } else {
+            c->wd_host = (unsigned int*)hp;   // (unified addressing: the same pointer is valid on the device)
+            *c->wd_host = 0;
+        }
+    }
     if (rc == ZRB_OK) rc = dalloc(c, &c->emb_first, (size_t)V);
     if (rc == ZRB_OK) rc = dalloc(c, &c->y_dev, N);
     if (rc == ZRB_OK) rc = dalloc(c, &c->x_dev, N);
@@ -139,6 +167,7 @@ void zrb_ctx_destroy(zrb_ctx* c) {
     for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (void* p : c->allocs) cudaFree(p);
+    if (c->wd_host) cudaFreeHost(c->wd_host);
     delete c;
 }
 
@@ -156,8 +185,14 @@ int zrb_set_lazy_update(zrb_ctx* c, int32_t on) {
     return ZRB_OK;
 }
 
+int zrb_check_health(zrb_ctx* c) {
+    ZRB_REQUIRE(c, "null ctx");
+    return watchdog_check(c);
+}
+
 int zrb_flush_updates(zrb_ctx* c, void* stream) {
     ZRB_REQUIRE(c, "null ctx");
+    ZRB_TRY(watchdog_check(c));
     if (c->cfg.engine != ZRB_ENGINE_TC) return ZRB_OK;
     return tc_flush_updates(c, (cudaStream_t)stream);
 }
@@ -343,6 +378,7 @@ int zrb_embed_scatter_rows(zrb_ctx* c, float* grad_embed, const int64_t* ids, co
 int zrb_train_step_update(zrb_ctx* c, const zrb_params* p, const zrb_params* g, float lr, float max_norm,
                           float* norm_out, void* stream) {
     ZRB_REQUIRE(c && p && g, "null argument");
+    ZRB_TRY(watchdog_check(c));
     ZRB_REQUIRE(c->cfg.layers * 4 + 3 <= 16, "fused step supports at most 3 layers");
     TensorList tl = param_list(c, p, g);
     if (c->cfg.engine == ZRB_ENGINE_TC) return tc_update(c, p, tl, lr, max_norm, norm_out, (cudaStream_t)stream);
@@ -381,7 +417,7 @@ int zrb_train_step_host(zrb_ctx* c, const zrb_params* p, const zrb_params* g, co
     ZRB_CUDA(cudaMemcpyAsync(h_loss, d_loss, sizeof(float), cudaMemcpyDeviceToHost, s));
     if (h_norm) ZRB_CUDA(cudaMemcpyAsync(h_norm, d_norm, sizeof(float), cudaMemcpyDeviceToHost, s));
     ZRB_CUDA(cudaStreamSynchronize(s));
-    return ZRB_OK;
+    return watchdog_check(c);   // this step's kernels have finished: report a give-up now, not at the next call
 }
 
 int zrb_lstm_layer_fwd(zrb_ctx* c, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,

@@ -54,6 +54,8 @@ struct zrb_ctx {
     int64_t emb_prev_cap = 0;              // capacity of emb_prev_ids (tokens)
     unsigned int* resident_flag = nullptr; // written by the backward recurrence kernel once all its CTAs are resident
     unsigned int resident_seq = 0;         // value the last launch publishes there
+    unsigned int* wd_flag = nullptr;       // watchdog of the persistent kernels (rec_common.cuh): device word, = resident_flag + 2
+    unsigned int* wd_host = nullptr;       // ... and the mapped host word the host polls (watchdog_check)
     int64_t* emb_prev_ids = nullptr;       // token ids whose gradient rows are non-zero in emb_prev_grad
     int emb_prev_n = 0;
     float* emb_prev_grad = nullptr;

@@ -79,6 +79,12 @@ static int tc_alloc(zrb_ctx* c, T** p, size_t count) {
     return ZRB_OK;
 }
 
+static inline RecWatchdog tc_watchdog(const zrb_ctx* c) {
+    RecWatchdog wd;
+    wd.flag = c->wd_flag; wd.host = c->wd_host;
+    return wd;
+}
+
 int tc_ctx_init(zrb_ctx* c) {
     int major = 0, dev = 0;
     cudaGetDevice(&dev);
@@ -223,7 +229,7 @@ int tc_forward(zrb_ctx* c, const zrb_params* p, const int64_t* x, const zrb_stat
                 ZRB_CUDA(cudaMemsetAsync(t->counter, 0, sizeof(unsigned int), s));
                 t->cnt_f = 0;
             }
-            ZRB_TRY(lstm_rec_fwd(t->fplan, t->w_img_f[l], t->h0_img[l], t->h_img, G, c->c0s[l], c->cst[l], out->h[l],
+            ZRB_TRY(lstm_rec_fwd(t->fplan, tc_watchdog(c), t->w_img_f[l], t->h0_img[l], t->h_img, G, c->c0s[l], c->cst[l], out->h[l],
                                  out->c[l], t->hprev_h[l], t->x_h[l + 1], t->counter, t->cnt_f, T, B, H, Hp, m, s,
                                  t->trace));
             t->cnt_f += arrivals;
@@ -353,7 +359,7 @@ static int tc_backward_layer(zrb_ctx* c, const zrb_params* p, const zrb_params* 
                 ZRB_CUDA(cudaMemsetAsync(t->counter + 32, 0, sizeof(unsigned int), s));
                 t->cnt_b = 0;
             }
-            ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], dG_h,
+            ZRB_TRY(lstm_rec_bwd(t->bplan, tc_watchdog(c), t->w_img_b[l], t->g_img, dY, c->gates[l], c->cst[l], c->c0s[l], dG_h,
                                  t->counter + 32, t->cnt_b, T, B, H, G4p, m, s,
                                  t->trace ? t->trace + 8 + (size_t)c->cfg.max_seq * 8 : nullptr, g->b_ih[l], g->b_hh[l],
                                  c->resident_flag, ++c->resident_seq, c->dG /* [N,4H] fp32, idle on this path */));
@@ -498,7 +504,7 @@ int tc_layer_fwd(zrb_ctx* c, const float* w_ih, const float* w_hh, const float* 
         t->cnt_f = 0;
     }
     MaskSrc m = make_mask_src(nullptr, 0, 0, 0, 0.f, 0);    // no dropout at this level: the caller applies it (model.py:105,108)
-    ZRB_TRY(lstm_rec_fwd(t->fplan, t->w_img_f[0], t->h0_img[0], t->h_img, c->gates[0], c->c0s[0], c->cst[0], hT, cT,
+    ZRB_TRY(lstm_rec_fwd(t->fplan, tc_watchdog(c), t->w_img_f[0], t->h0_img[0], t->h_img, c->gates[0], c->c0s[0], c->cst[0], hT, cT,
                          t->hprev_h[0], t->x_h[1], t->counter, t->cnt_f, T, B, H, Hp, m, s, nullptr, y));
     t->cnt_f += arrivals;
     c->have_fwd = false;                         // a model-level backward must not follow this
@@ -520,7 +526,7 @@ int tc_layer_bwd(zrb_ctx* c, const float* dy, float* dx, float* dw_ih, float* dw
         t->cnt_b = 0;
     }
     MaskSrc m = make_mask_src(nullptr, 0, 0, 0, 0.f, 0);
-    ZRB_TRY(lstm_rec_bwd(t->bplan, t->w_img_b[0], t->g_img, dy, c->gates[0], c->cst[0], c->c0s[0], t->dG_h, t->counter + 32,
+    ZRB_TRY(lstm_rec_bwd(t->bplan, tc_watchdog(c), t->w_img_b[0], t->g_img, dy, c->gates[0], c->cst[0], c->c0s[0], t->dG_h, t->counter + 32,
                          t->cnt_b, T, B, H, G4p, m, s, nullptr, db_ih, db_hh, c->resident_flag, ++c->resident_seq, c->dG));
     t->cnt_b += arrivals;
     const float inv = 1.f / kGradScale;

@@ -46,6 +46,7 @@ struct RecBwdArgs {
     int T, B, H, G4p, U, G, GB, Kc, nCTA;
     int KcS, GBi;             // K chunks per CTA (Kc / S); 8-row batch groups of the dG images (GB, or 4 when N = 32)
     MaskSrc m;
+    RecWatch w;               // watchdog (rec_common.cuh)
     long long* trace;         // optional (profiling): [8] launch stamps (rec_launch_stamps) + [T][8] clock64 stamps of CTA 0
 };
 
@@ -157,15 +158,17 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
         pdl_wait();   // everything below reads what the preceding kernel wrote
+        bool dead = false;
         const int lbo_b = a.GBi * 128;
         const size_t gate_bytes = (size_t)a.Kc * a.GBi * 128;   // one gate's whole dG image
         const bool publish = a.res_flag != nullptr && blockIdx.x == 0;
         if (publish && T == 1) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.res_flag), "r"(a.res_value) : "memory");
         for (int s = 1; s < T; ++s) {
             const int t = T - 1 - s;                      // step being computed; needs dG_{t+1}
-            grid_counter_wait(a.counter, a.base + (unsigned int)s * a.nCTA);
-            if (publish && s == 1)   // every CTA arrived once: the whole grid is resident
+            grid_counter_wait(a.counter, a.base + (unsigned int)s * a.nCTA, a.w, dead, s);
+            if (publish && s == 1)   // every CTA arrived once: the whole grid is resident (or gave up: a stream gated on this must not hang)
                 asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.res_flag), "r"(a.res_value) : "memory");
+            if (dead) break;   // (watchdog: a thread that gave up starts no further asynchronous operation)
             if (tr) trs[s * 8 + 0] = clock64();
             fence_proxy_async_global();
             const uint8_t* img = (const uint8_t*)a.g_img + ((size_t)((t + 1) & 1) * 4 + gate) * gate_bytes +
@@ -185,10 +188,12 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         const uint32_t idesc = make_idesc_f16(S == 2 ? 128 : 64, Bp, 0, 0);
         const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
         const uint32_t lbo_a = a.G * 128, lbo_b = a.GBi * 128;
-        bounded_mbar_wait(bar_a, 0);
-        for (int s = 1; s < T; ++s) {
+        bool dead = false;
+        bounded_mbar_wait(bar_a, 0, a.w, dead, kWaitWeights, 0);
+        for (int s = 1; s < T && !dead; ++s) {
             for (int pc = 0; pc < kRecPieces; ++pc) {
-                bounded_mbar_wait(&bar_b[pc], (s - 1) & 1);
+                bounded_mbar_wait(&bar_b[pc], (s - 1) & 1, a.w, dead, kWaitOperand, s);
+                if (dead) break;
                 tcgen05_fence_after();
                 if (tr && pc == 0 && me == 0) trs[s * 8 + 1] = clock64();
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     umma_f16(my_acc, da, db, idesc, ks >= kRecMmaWarps ? 1u : 0u);
                 }
             }
-            umma_commit(bar_mma);
+            if (!dead) umma_commit(bar_mma);
             if (tr && me == 0) trs[s * 8 + 2] = clock64();
         }
     } else if (warp < kRecEpiWarps) {
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
         if (threadIdx.x == 0) pdl_launch_dependents();   // after the wait: dependents of this kernel keep stream order with its predecessor
         // ===================== epilogue: 256 threads, cells (u, b) of this CTA's U units =====================
         const int tid = threadIdx.x;
+        bool dead = false;
         const int cells = a.U * B;                     // cell = b * U + u (u fastest: contiguous j)
         float dcreg[kRecMaxCell], bsum[kRecMaxCell][4];
 #pragma unroll
@@ -249,8 +255,8 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                 }
             }
             if (s > 0) {
-                if (push && tid == 0) mbar_expect_tx(bar_recv, recv_bytes);
-                bounded_mbar_wait(bar_mma, (s - 1) & 1);
+                if (push && tid == 0 && !dead) mbar_expect_tx(bar_recv, recv_bytes);
+                bounded_mbar_wait(bar_mma, (s - 1) & 1, a.w, dead, kWaitAcc, s);
                 tcgen05_fence_after();
                 if (tr && tid == 0) trs[s * 8 + 3] = clock64();
                 // TMEM -> own shared staging: accumulator row i (cluster-local unit) in lane (i%16)+32*(i/16)
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                                 float* dst = sD + row * ldd + c0;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) dst[i] = acc[i];
-                            } else if (row < UC) {
+                            } else if (row < UC && !dead) {
                                 // straight from the registers into the shared memory of the CTA that owns this unit
                                 const int owner = row / a.U, uo = row - owner * a.U;
                                 const uint32_t dst = mapa_shared(sR_addr + (uint32_t)((((int)rank * a.U + uo) * ldr + c0) * 4), owner);
@@ -300,17 +306,13 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
                     if (tid < 4) mbar_arrive_remote_release(mapa_shared(bar_part_addr, tid));
                     {   // wait until all four CTAs of the cluster staged their partials
                         uint32_t n = 0; long long t0 = 0;
-                        while (!mbar_try_wait_acq_cluster(bar_part, (s - 1) & 1)) {
-                            if ((++n & 0xFFFu) == 0) {
-                                long long now = clock64();
-                                if (t0 == 0) t0 = now;
-                                else if (now - t0 > kSpinCycles) asm volatile("trap;");
-                            }
+                        while (!dead && !mbar_try_wait_acq_cluster(bar_part, (s - 1) & 1)) {
+                            if ((++n & 0xFFFu) == 0 && rec_spin_check(a.w, t0, kWaitPart, s)) dead = true;
                         }
                     }
                 } else {
                     if (tr && tid == 0) trs[s * 8 + 4] = clock64();
-                    bounded_mbar_wait(bar_recv, (s - 1) & 1);   // all CS x U x Bp partial sums of my units have landed
+                    bounded_mbar_wait(bar_recv, (s - 1) & 1, a.w, dead, kWaitRecv, s);   // all CS x U x Bp partial sums of my units have landed
                 }
             }
             if (tr && tid == 0) trs[s * 8 + 5] = clock64();
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             if (tr && tid == 0) trs[s * 8 + 6] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
-                grid_counter_arrive(a.counter);
+                if (!(a.w.fault_step == s && blockIdx.x == 1)) grid_counter_arrive(a.counter);   // (fault injection: tests only)
                 if (tr) trs[s * 8 + 7] = clock64();
             }
             // off the critical path: row-major image for the batched dgrad / wgrad GEMMs
@@ -443,7 +445,7 @@ static bool rec_bwd_no_coop() {
     // Profilers (Nsight Compute) refuse cooperative + cluster launches; under one (detected through the injection
     // environment it sets up) or with ZRB_NO_COOP=1 the kernel is launched as a plain cluster launch after an occupancy
     // check that the whole grid fits the device.  Without the cooperative guarantee another context holding SMs (MPS, a
-    // concurrent kernel) could leave CTAs unscheduled; the barrier waits are bounded and trap after ~3 s instead of hanging.
+    // concurrent kernel) could leave CTAs unscheduled; the barrier waits are bounded: after ~3 s the kernel gives up and reports it (rec_common.cuh: RecWatch) instead of hanging.
     static const bool v = getenv("ZRB_NO_COOP") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
                           getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NVTX_INJECTION64_PATH") != nullptr;
     return v;
@@ -591,7 +593,7 @@ static int launch_rec_bwd(const RecPlan& p, const RecBwdArgs& a, cudaStream_t s)
     return ZRB_OK;
 }
 
-int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
+int lstm_rec_bwd(const RecPlan& p, const RecWatchdog& wd, const __half* w_img, __half* g_img, const float* dy, const float* gates,
                  const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
                  int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace, float* db1, float* db2,
                  unsigned int* resident_flag, unsigned int resident_value, float* db_scratch) {
@@ -604,6 +606,8 @@ int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const flo
     a.counter = counter; a.db1 = db1; a.db2 = db2; a.db_scratch = db_scratch; a.res_flag = resident_flag; a.res_value = resident_value;
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     a.KcS = p.KcS; a.GBi = p.GBi;
+    ZRB_REQUIRE(wd.flag && wd.host, "lstm_rec_bwd needs the context's watchdog words");
+    a.w = rec_watch_args(wd, "bwd");
     if (trace) ZRB_CUDA(cudaMemsetAsync(trace + 4, 0x80, 2 * sizeof(long long), s));
     return p.KS == 2 ? launch_rec_bwd<2>(p, a, s) : launch_rec_bwd<1>(p, a, s);
 }

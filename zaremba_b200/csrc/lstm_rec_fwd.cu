@@ -62,6 +62,7 @@ struct RecFwdArgs {
     int T, B, H, Hp, U, G, GB, Kc, nCTA;
     int KcS, GBi;             // K chunks per CTA (Kc / KS); 8-row batch groups of the operand image (GB, or 4 when N = 32)
     MaskSrc m;
+    RecWatch w;               // watchdog (rec_common.cuh)
     long long* trace;         // optional (profiling): [8] launch stamps (rec_launch_stamps) + [T][8] clock64 stamps of CTA 0
 };
 
@@ -135,10 +136,12 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         mbar_expect_tx(bar_a, a_bytes);
         for (int off = 0; off < a_bytes; off += 32768) bulk_load_1d(sA + off, src + off, min(32768, a_bytes - off), bar_a);
         pdl_wait();   // everything below reads what the preceding kernel wrote
+        bool dead = false;
         const int lbo_b = a.GBi * 128;
         const size_t img_bytes = (size_t)a.Kc * a.GBi * 128;   // one whole h image; this CTA reads K chunks [rank*KcS, +KcS)
         for (int t = 0; t < a.T; ++t) {
-            if (t > 0) grid_counter_wait(a.counter, a.base + (unsigned int)t * a.nCTA);
+            if (t > 0) grid_counter_wait(a.counter, a.base + (unsigned int)t * a.nCTA, a.w, dead, t);
+            if (dead) break;   // (watchdog: a thread that gave up starts no further asynchronous operation)
             if (tr) trs[t * 8 + 0] = clock64();
             fence_proxy_async_global();
             const uint8_t* img = (t == 0 ? (const uint8_t*)a.h0_img : (const uint8_t*)a.h_img + (size_t)t * img_bytes) +
@@ -158,10 +161,12 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         const uint32_t idesc = make_idesc_f16(SPLIT ? 128 : 64, Bp, 0, 0);
         const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
         const uint32_t lbo_a = a.G * 128, lbo_b = a.GBi * 128;
-        bounded_mbar_wait(bar_a, 0);
-        for (int t = 0; t < a.T; ++t) {
+        bool dead = false;
+        bounded_mbar_wait(bar_a, 0, a.w, dead, kWaitWeights, 0);
+        for (int t = 0; t < a.T && !dead; ++t) {
             for (int pc = 0; pc < kRecPieces; ++pc) {
-                bounded_mbar_wait(&bar_b[pc], t & 1);
+                bounded_mbar_wait(&bar_b[pc], t & 1, a.w, dead, kWaitOperand, t);
+                if (dead) break;
                 tcgen05_fence_after();
                 if (tr && pc == 0 && me == 0) trs[t * 8 + 1] = clock64();
                 const int k0 = pc * piece_steps, k1 = min(ksteps, k0 + piece_steps);
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                     umma_f16(my_acc, da, db, idesc, ks >= kRecMmaWarps ? 1u : 0u);
                 }
             }
-            umma_commit(bar_mma);
+            if (!dead) umma_commit(bar_mma);
             if (tr && me == 0) trs[t * 8 + 2] = clock64();
         }
     } else if (warp < kRecEpiWarps) {
@@ -180,6 +185,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         // ===================== epilogue: 256 threads =====================
         const int tid = threadIdx.x;
         const int B = a.B, H = a.H;
+        bool dead = false;
         const int cells = a.U * B;                     // cell = b * U + u (u fastest: contiguous j)
         const uint64_t n_total = (uint64_t)a.T * B * H;
         float creg[kRecMaxCell];
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
         const int rows_pair = 8 * a.U;                                   // K-split: gate rows of the pair (4 x 2U)
         const uint32_t recv_bytes = 2u * 4u * (uint32_t)a.U * (uint32_t)Bp * 4u;   // 2 sources x 4U rows x Bp columns
         for (int t = 0; t < a.T; ++t) {
-            if (SPLIT && tid == 0) mbar_expect_tx(bar_recv, recv_bytes);
+            if (SPLIT && tid == 0 && !dead) mbar_expect_tx(bar_recv, recv_bytes);
             // prefetch the x-part pre-activations of this step while the MMAs run
             float pre[kRecMaxCell][4];
 #pragma unroll
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 for (int q = 0; q < 4; ++q)
                     pre[k][q] = ok ? __ldg(a.gates + ((size_t)t * B + b) * 4 * H + (size_t)q * H + j0 + u) : 0.f;
             }
-            bounded_mbar_wait(bar_mma, t & 1);
+            bounded_mbar_wait(bar_mma, t & 1, a.w, dead, kWaitAcc, t);
             tcgen05_fence_after();
             if (tr && tid == 0) trs[t * 8 + 3] = clock64();
             {   // 8 warps share the (TMEM lane quadrant, 8-column group) tasks; each sums ALL issuers' accumulators
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                     } else {
                         // row = 4 * (unit within the pair) + gate: straight into the shared memory of the owning CTA
                         const int row = 32 * quad + lane;
-                        if (row < rows_pair) {
+                        if (row < rows_pair && !dead) {
                             // receive rows are gate-major (q * U + u): the cell threads of a warp (consecutive u) then read
                             // addresses ldr floats apart, 4 banks apart, instead of 4 * ldr (2 distinct banks: 16-way conflicts)
                             const int up = row >> 2, owner = up / a.U, lrow = (row & 3) * a.U + (up - owner * a.U);
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
                 if (tr && tid == 0) trs[t * 8 + 4] = clock64();
             } else {
                 if (tr && tid == 0) trs[t * 8 + 4] = clock64();
-                bounded_mbar_wait(bar_recv, t & 1);   // both K halves of my 4U rows have landed
+                bounded_mbar_wait(bar_recv, t & 1, a.w, dead, kWaitRecv, t);   // both K halves of my 4U rows have landed
             }
             float o_i[kRecMaxCell], o_f[kRecMaxCell], o_g[kRecMaxCell], o_o[kRecMaxCell], o_h[kRecMaxCell];
 #pragma unroll
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_fwd_kernel(RecFwdArgs
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
                 if (tr) trs[t * 8 + 6] = clock64();
-                grid_counter_arrive(a.counter);
+                if (!(a.w.fault_step == t && cta == 1)) grid_counter_arrive(a.counter);   // (fault injection: tests only)
                 if (tr) trs[t * 8 + 7] = clock64();
             }
             // off the critical path: what backward and the next layer read after this kernel
@@ -420,7 +426,7 @@ int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStrea
     return ZRB_OK;
 }
 
-int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
+int lstm_rec_fwd(const RecPlan& p, const RecWatchdog& wd, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
                  const float* c0, float* cst, float* h_last, float* c_last, __half* hprev_h, __half* y_h,
                  unsigned int* counter, unsigned int counter_base, int T, int B, int H, int Hp, MaskSrc m, cudaStream_t s,
                  long long* trace, float* h_f32) {
@@ -439,6 +445,8 @@ int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __
     a.T = T; a.B = B; a.H = H; a.Hp = Hp; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m;
     a.KcS = p.KcS; a.GBi = p.GBi;
     a.trace = trace;
+    ZRB_REQUIRE(wd.flag && wd.host, "lstm_rec_fwd needs the context's watchdog words");
+    a.w = rec_watch_args(wd, "fwd");
     if (trace) ZRB_CUDA(cudaMemsetAsync(trace + 4, 0x80, 2 * sizeof(long long), s));
     if (p.KS == 1) {
         void* args[] = {&a};

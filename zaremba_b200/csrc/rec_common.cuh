@@ -1,5 +1,6 @@
 // Helpers shared by the persistent recurrence kernels (forward / backward).
 #pragma once
+#include <string.h>
 #include "tc_common.cuh"
 #include "tc_kernels.h"
 
@@ -25,17 +26,60 @@ constexpr int kRecPieces = 4;                         // operand image arrives i
                                                       // longer arrival; issuing both drain tasks' TMEM loads before one wait
                                                       // was also slower than two rounds.)
 constexpr int kRecMaxCell = 2;                        // (unit, batch) cells per epilogue thread
-constexpr long long kSpinCycles = 6000000000ll;  // ~3 s at 2 GHz: a lost wake-up traps instead of hanging the GPU
+// ---- watchdog -------------------------------------------------------------------------------------
+// Every wait of the persistent kernels is bounded.  A wait that runs out (a lost wake-up, a grid that is not co-resident)
+// publishes a code in the context's abort word; from then on EVERY wait of EVERY thread returns at once (a thread that
+// has seen the word set stops waiting for good), so the kernel runs to its end through its unchanged barrier skeleton --
+// producing garbage, but terminating, with the CUDA context intact.  The host finds the code in a mapped host word at its
+// next API call and fails the zrb context (api.cu: watchdog_check).  Nothing on the fast path but a register test.
+struct RecWatch {
+    unsigned int* flag;       // device word polled by the spinning threads (0 = healthy)
+    unsigned int* host;       // mapped host word the first thread to give up writes the code to
+    long long spin_cycles;    // ~3 s at 2 GHz unless ZRB_SPIN_CYCLES says otherwise
+    int fault_step;           // fault injection for the tests (ZRB_FAULT_SKIP_ARRIVE): CTA 1 skips this step's arrival; -1 = off
+};
+// host: the kernel argument for one launch.  ZRB_SPIN_CYCLES shortens the time-out, ZRB_FAULT_SKIP_ARRIVE="fwd:3" /
+// "bwd:3" makes CTA 1 of that kernel skip its arrival at step 3 (tests/test_gpu_watchdog.py) -- both read once.
+static inline RecWatch rec_watch_args(const RecWatchdog& wd, const char* which) {
+    static const long long spin = [] { const char* e = getenv("ZRB_SPIN_CYCLES"); long long v = e ? atoll(e) : 0; return v > 0 ? v : 6000000000ll; }();
+    static const char* fault = getenv("ZRB_FAULT_SKIP_ARRIVE");
+    RecWatch w;
+    w.flag = wd.flag; w.host = wd.host; w.spin_cycles = spin;
+    w.fault_step = (fault && !strncmp(fault, which, 3) && fault[3] == ':') ? atoi(fault + 4) : -1;
+    return w;
+}
+enum { kWaitWeights = 1, kWaitOperand = 2, kWaitAcc = 3, kWaitRecv = 4, kWaitGrid = 5, kWaitPart = 6 };
 
-__device__ __forceinline__ void bounded_mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// code = wait kind | CTA << 8 | step << 20
+static __device__ __noinline__ void rec_give_up(const RecWatch& w, int kind, int step) {
+    const unsigned int code = (unsigned int)kind | ((unsigned int)(blockIdx.x & 0xFFF) << 8) | ((unsigned int)(step & 0xFFF) << 20);
+    if (atomicCAS(w.flag, 0u, code) == 0u) {
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(w.host), "r"(code) : "memory");
+        __threadfence_system();
+    }
+}
+// one slow-path visit of a spinning thread: true = stop waiting (for good)
+__device__ __forceinline__ bool rec_spin_check(const RecWatch& w, long long& t0, int kind, int step) {
+    if (ld_relaxed_gpu(w.flag) != 0u) return true;
+    const long long now = clock64();
+    if (t0 == 0) { t0 = now; return false; }
+    if (now - t0 <= w.spin_cycles) return false;
+    rec_give_up(w, kind, step);
+    return true;
+}
+
+__device__ __forceinline__ void bounded_mbar_wait(uint64_t* bar, uint32_t parity, const RecWatch& w, bool& dead, int kind,
+                                                  int step) {
+    if (dead) return;
     uint32_t n = 0;
     long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++n & 0xFFFu) == 0) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > kSpinCycles) asm volatile("trap;");
-        }
+        if ((++n & 0xFFFu) == 0 && rec_spin_check(w, t0, kind, step)) { dead = true; return; }
     }
 }
 
@@ -80,21 +124,14 @@ __device__ __forceinline__ void grid_counter_arrive(unsigned int* counter) {
 }
 
 // spin on a global counter (grid barrier): relaxed polls (a plain L2 round trip each; ld.acquire would add an L1
-// invalidate per poll), one acquire fence after the last arrival was seen; same bounded wait
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void grid_counter_wait(const unsigned int* counter, unsigned int target) {
+// invalidate per poll), one acquire fence after the last arrival was seen; bounded like the mbarrier waits
+__device__ __forceinline__ void grid_counter_wait(const unsigned int* counter, unsigned int target, const RecWatch& w,
+                                                  bool& dead, int step) {
+    if (dead) return;
     uint32_t n = 0;
     long long t0 = 0;
     while (ld_relaxed_gpu(counter) < target) {
-        if ((++n & 0x3FFu) == 0) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > kSpinCycles) asm volatile("trap;");
-        }
+        if ((++n & 0x3FFu) == 0 && rec_spin_check(w, t0, kWaitGrid, step)) { dead = true; return; }
     }
     asm volatile("fence.acquire.gpu;" ::: "memory");
 }

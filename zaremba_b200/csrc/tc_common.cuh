@@ -20,7 +20,7 @@ namespace zrb {
 //                   running (pdl_wait in the kernels).  9 us per train step at the Large config; the cooperative
 //                   attribute suppresses the early start (measured: no gain with both attributes).
 // A plain launch is only as safe as the occupancy check: two persistent grids launched at the same time from two
-// streams could each get part of the device and spin on their barriers (until the bounded waits trap).  So the default
+// streams could each get part of the device and spin on their barriers (until the bounded waits give up and fail the zrb context).  So the default
 // is programmatic only while ONE tcgen05 context is alive on the device -- a process that holds several (an ensemble,
 // two trainers) gets the cooperative launch.  ZRB_REC_PDL=0 forces cooperative, =1 forces programmatic.
 static inline int rec_pdl_env() {

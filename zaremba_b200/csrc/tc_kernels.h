@@ -34,12 +34,18 @@ struct RecPlan {
     int GBi;     // 8-row batch groups of the operand images (GB, or padded so that the MMA's N is a multiple of 16)
 };
 size_t rec_smem_bytes(int Kc, int G, int GB);
+// Where a persistent kernel that gave up on a wait (rec_common.cuh: RecWatch) reports it: `flag` is the device word the
+// spinning threads poll, `host` a mapped host word the host reads without synchronising.  Owned by the context.
+struct RecWatchdog {
+    unsigned int* flag = nullptr;
+    unsigned int* host = nullptr;
+};
 int rec_fwd_plan(int H, int B, RecPlan* plan);
 int pack_whh_fwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s);
 // h0_img: the B operand of step 0 (image of the state entering the window, built by fwd_prep); h_img slot t+1 is
 // written by step t.  The grid-barrier counter is never reset between launches: `counter_base` is its value when
 // the launch starts (the caller adds T * nCTA per launch).
-int lstm_rec_fwd(const RecPlan& p, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
+int lstm_rec_fwd(const RecPlan& p, const RecWatchdog& wd, const __half* w_img, const __half* h0_img, __half* h_img, float* gates,
                  const float* c0, float* cst, float* h_last, float* c_last, __half* hprev_h, __half* y_h,
                  unsigned int* counter, unsigned int counter_base, int T, int B, int H, int Hp, MaskSrc m, cudaStream_t s,
                  long long* trace = nullptr, float* h_f32 = nullptr);   // h_f32: optional [N,H] fp32 copy of h_t
@@ -65,7 +71,7 @@ int update_pack(float* p, float* g, int rows, int cols, float lr, const float* s
                 bool pdl = false);   // pdl: programmatic dependent of the (forward recurrence) kernel enqueued before it
 int rec_bwd_plan(int H, int B, RecPlan* plan);   // U = units per CTA, nCTA = 4 * clusters
 int pack_whh_bwd(const float* W, __half* img, int H, const RecPlan& p, cudaStream_t s);
-int lstm_rec_bwd(const RecPlan& p, const __half* w_img, __half* g_img, const float* dy, const float* gates,
+int lstm_rec_bwd(const RecPlan& p, const RecWatchdog& wd, const __half* w_img, __half* g_img, const float* dy, const float* gates,
                  const float* cst, const float* c0, __half* dG_h, unsigned int* counter, unsigned int counter_base, int T,
                  int B, int H, int G4p, MaskSrc m, cudaStream_t s, long long* trace = nullptr, float* db1 = nullptr,
                  float* db2 = nullptr,    // db1 / db2: bias gradients sum_{t,b} dG [4H] written by the kernel (or null)

@@ -273,6 +273,11 @@ class Trainer:
             _lib.check(_lib.load().zrb_params_changed(self.ctx))
             self._versions = v
 
+    def check_health(self):
+        """Raise if a persistent recurrence kernel gave up on a wait (zrb_check_health: one host load, no sync).  Every
+        train / eval call checks this on entry anyway; this is for loops that never read anything back."""
+        _lib.check(_lib.load().zrb_check_health(self.ctx))
+
     def close(self):
         """Release the copy-engine transport (IPC mappings, streams)."""
         if getattr(self, "_dp", None) is not None:
