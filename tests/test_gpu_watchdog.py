@@ -1,7 +1,7 @@
 """Watchdog of the persistent recurrence kernels (include/zaremba_b200.h: zrb_check_health; csrc/rec_common.cuh: RecWatch).
 
-Fault injection: ZRB_FAULT_SKIP_ARRIVE="fwd:3" / "bwd:3" makes CTA 1 of that kernel skip its grid-barrier arrival at step 3,
-so every CTA waits for a count that never comes -- the lost wake-up the bounded waits exist for.  With the time-out cut
+Fault injection: ZRB_FAULT_BARRIER_BASE="fwd" / "bwd" makes that kernel's launches expect one grid-barrier arrival more
+than the grid delivers, so every CTA waits for a count that never comes -- the lost wake-up the bounded waits exist for.  With the time-out cut
 to ~20 ms (ZRB_SPIN_CYCLES) the kernel must (1) terminate instead of hanging or trapping, (2) leave the CUDA context
 usable, (3) make the next library call fail with ZRB_E_CUDA naming the wait.  Runs in a subprocess: the switches are read
 once per process.
@@ -50,7 +50,7 @@ print("WATCHDOG_OK", round(dt, 3), msg[:160])
 def test_lost_arrival_is_reported_not_fatal(which):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
-    env = dict(os.environ, ZRB_FAULT_SKIP_ARRIVE=f"{which}:3", ZRB_SPIN_CYCLES="40000000")
+    env = dict(os.environ, ZRB_FAULT_BARRIER_BASE=which, ZRB_SPIN_CYCLES="40000000")
     r = subprocess.run([sys.executable, "-c", SCRIPT % ROOT], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "WATCHDOG_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
 

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kRecThreads, 1) lstm_rec_bwd_kernel(RecBwdArgs
             if (tr && tid == 0) trs[s * 8 + 6] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
-                if (!(a.w.fault_step == s && blockIdx.x == 1)) grid_counter_arrive(a.counter);   // (fault injection: tests only)
+                grid_counter_arrive(a.counter);
                 if (tr) trs[s * 8 + 7] = clock64();
             }
             // off the critical path: row-major image for the batched dgrad / wgrad GEMMs
@@ -607,7 +607,8 @@ int lstm_rec_bwd(const RecPlan& p, const RecWatchdog& wd, const __half* w_img, _
     a.T = T; a.B = B; a.H = H; a.G4p = G4p; a.U = p.U; a.G = p.G; a.GB = p.GB; a.Kc = p.Kc; a.nCTA = p.nCTA; a.m = m; a.trace = trace;
     a.KcS = p.KcS; a.GBi = p.GBi;
     ZRB_REQUIRE(wd.flag && wd.host, "lstm_rec_bwd needs the context's watchdog words");
-    a.w = rec_watch_args(wd, "bwd");
+    a.w = rec_watch_args(wd);
+    a.base += rec_fault_base("bwd");   // (tests only)
     if (trace) ZRB_CUDA(cudaMemsetAsync(trace + 4, 0x80, 2 * sizeof(long long), s));
     return p.KS == 2 ? launch_rec_bwd<2>(p, a, s) : launch_rec_bwd<1>(p, a, s);
 }

@@ -36,17 +36,19 @@ struct RecWatch {
     unsigned int* flag;       // device word polled by the spinning threads (0 = healthy)
     unsigned int* host;       // mapped host word the first thread to give up writes the code to
     long long spin_cycles;    // ~3 s at 2 GHz unless ZRB_SPIN_CYCLES says otherwise
-    int fault_step;           // fault injection for the tests (ZRB_FAULT_SKIP_ARRIVE): CTA 1 skips this step's arrival; -1 = off
 };
-// host: the kernel argument for one launch.  ZRB_SPIN_CYCLES shortens the time-out, ZRB_FAULT_SKIP_ARRIVE="fwd:3" /
-// "bwd:3" makes CTA 1 of that kernel skip its arrival at step 3 (tests/test_gpu_watchdog.py) -- both read once.
-static inline RecWatch rec_watch_args(const RecWatchdog& wd, const char* which) {
+// host: the kernel argument for one launch (ZRB_SPIN_CYCLES shortens the time-out; read once), and the fault injection
+// of tests/test_gpu_watchdog.py: ZRB_FAULT_BARRIER_BASE="fwd" / "bwd" makes that kernel's launches expect one arrival
+// more than the grid will ever deliver -- every CTA then sits at its first grid barrier like after a lost wake-up.
+static inline RecWatch rec_watch_args(const RecWatchdog& wd) {
     static const long long spin = [] { const char* e = getenv("ZRB_SPIN_CYCLES"); long long v = e ? atoll(e) : 0; return v > 0 ? v : 6000000000ll; }();
-    static const char* fault = getenv("ZRB_FAULT_SKIP_ARRIVE");
     RecWatch w;
     w.flag = wd.flag; w.host = wd.host; w.spin_cycles = spin;
-    w.fault_step = (fault && !strncmp(fault, which, 3) && fault[3] == ':') ? atoi(fault + 4) : -1;
     return w;
+}
+static inline unsigned int rec_fault_base(const char* which) {
+    static const char* fault = getenv("ZRB_FAULT_BARRIER_BASE");
+    return (fault && !strcmp(fault, which)) ? 1u : 0u;
 }
 enum { kWaitWeights = 1, kWaitOperand = 2, kWaitAcc = 3, kWaitRecv = 4, kWaitGrid = 5, kWaitPart = 6 };
 
@@ -56,20 +58,20 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
     return v;
 }
 // code = wait kind | CTA << 8 | step << 20
-static __device__ __noinline__ void rec_give_up(const RecWatch& w, int kind, int step) {
+static __device__ __noinline__ void rec_give_up(unsigned int* flag, unsigned int* host, int kind, int step) {
     const unsigned int code = (unsigned int)kind | ((unsigned int)(blockIdx.x & 0xFFF) << 8) | ((unsigned int)(step & 0xFFF) << 20);
-    if (atomicCAS(w.flag, 0u, code) == 0u) {
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(w.host), "r"(code) : "memory");
+    if (atomicCAS(flag, 0u, code) == 0u) {
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(host), "r"(code) : "memory");
         __threadfence_system();
     }
 }
-// one slow-path visit of a spinning thread: true = stop waiting (for good)
+// one slow-path visit of a spinning thread (every few thousand polls): true = stop waiting (for good)
 __device__ __forceinline__ bool rec_spin_check(const RecWatch& w, long long& t0, int kind, int step) {
     if (ld_relaxed_gpu(w.flag) != 0u) return true;
     const long long now = clock64();
     if (t0 == 0) { t0 = now; return false; }
     if (now - t0 <= w.spin_cycles) return false;
-    rec_give_up(w, kind, step);
+    rec_give_up(w.flag, w.host, kind, step);
     return true;
 }
 
